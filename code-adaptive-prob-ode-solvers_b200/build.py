@@ -1,0 +1,74 @@
+"""Builds libpn_b200.so (CUDA kernels + C ABI) in-tree with nvcc for sm_100a.
+
+    python code-adaptive-prob-ode-solvers_b200/build.py [--force]
+
+One translation unit per problem family, compiled in parallel; the shared library travels to the
+GPU box with the repository snapshot (it is git-ignored, not gpurun-ignored).
+"""
+
+import concurrent.futures
+import glob
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
+LIB = os.path.join(HERE, "libpn_b200.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-std=c++17", "-O3", "-lineinfo",
+    # fp64 contract: no implicit contraction; every FMA in the kernels is an explicit fma()
+    "-fmad=false", "-prec-div=true", "-prec-sqrt=true",
+    "-Xcompiler", "-fPIC",
+    "-diag-suppress", "177",
+]  # fmt: skip
+
+
+def _newest(paths):
+    return max(os.path.getmtime(p) for p in paths)
+
+
+def build(force=False, verbose=False):
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    if not os.path.exists(nvcc):
+        nvcc = "nvcc"
+    srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+    hdrs = glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h"))
+    hdrs += [os.path.join(HERE, "..", "include", "pn_b200.h"), os.path.abspath(__file__)]
+    os.makedirs(OBJ, exist_ok=True)
+    dep_time = _newest(hdrs)
+    jobs = []
+    objs = []
+    for s in srcs:
+        o = os.path.join(OBJ, os.path.basename(s)[:-3] + ".o")
+        objs.append(o)
+        if force or not os.path.exists(o) or os.path.getmtime(o) < max(dep_time, os.path.getmtime(s)):
+            jobs.append((s, o))
+
+    def compile_one(job):
+        s, o = job
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        return s, r.returncode, r.stdout + r.stderr
+
+    if jobs:
+        with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+            for s, rc, out in ex.map(compile_one, jobs):
+                if verbose or rc:
+                    sys.stderr.write(out)
+                if rc:
+                    raise RuntimeError(f"nvcc failed on {s}")
+    if jobs or not os.path.exists(LIB) or os.path.getmtime(LIB) < _newest(objs):
+        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("link failed")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,365 @@
+// pn_capi.cu -- C ABI (include/pn_b200.h) over the compiled kernel instances.
+//
+// What this replaces in the reference: the Python closure `solve_(u0, p)` of
+// src/odecheckpts/ivpsolvers.py:55-91 (Taylor initialisation :63-68, solve_adaptive_save_at
+// :71-77, backward marginalisation :80-81, QOI selection :84-89), batched over an ensemble.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/pn_b200.h"
+#include "pn_registry.h"
+
+namespace pn {
+
+static std::vector<KernelEntry>& table() {
+  static std::vector<KernelEntry> t;
+  return t;
+}
+void register_kernel(const KernelEntry& e) { table().push_back(e); }
+const KernelEntry* find_kernel(int family, int problem, int nu, int strategy) {
+  for (const auto& e : table())
+    if (e.family == family && e.problem == problem && e.nu == nu && e.strategy == strategy) return &e;
+  return nullptr;
+}
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+// Prior constant: lower Cholesky factor of the flipped Hilbert matrix Q1[i][j] = 1/(2nu-i-j+1)
+// (SURVEY A.1).  Factorised in extended precision and rounded once, so the table does not
+// depend on host compiler flags.
+static void prior_lq(int nu, double* lq /* n*n row-major */) {
+  const int n = nu + 1;
+  std::vector<long double> Lc((size_t)n * n, 0.0L);
+  for (int j = 0; j < n; ++j) {
+    long double s = 1.0L / (long double)(2 * nu - 2 * j + 1);
+    for (int k = 0; k < j; ++k) s -= Lc[j * n + k] * Lc[j * n + k];
+    long double djj = sqrtl(s);
+    Lc[j * n + j] = djj;
+    for (int i = j + 1; i < n; ++i) {
+      long double t = 1.0L / (long double)(2 * nu - i - j + 1);
+      for (int k = 0; k < j; ++k) t -= Lc[i * n + k] * Lc[j * n + k];
+      Lc[i * n + j] = t / djj;
+    }
+  }
+  for (int i = 0; i < n * n; ++i) lq[i] = (double)Lc[i];
+}
+
+struct Plan {
+  const KernelEntry* k = nullptr;
+  int grid = 0, ctas_per_sm = 0, num_sms = 0;
+  size_t smem = 0;
+  size_t ws_ticket = 256;  // bytes reserved for the work-queue ticket
+  size_t ws_cond = 0;      // bytes of conditionals
+};
+
+static int resolve(const pn_b200_desc* d, const KernelEntry** out) {
+  if (!d) return fail(PN_B200_ERR_ARGUMENT, "null descriptor");
+  if (d->batch < 0 || d->num_save_at < 2) return fail(PN_B200_ERR_ARGUMENT, "need batch >= 0 and at least 2 save_at points");
+  if (d->nu < 1 || d->nu > 8) return fail(PN_B200_ERR_UNSUPPORTED, "nu out of range");
+  if (d->strategy != PN_B200_FILTER && d->strategy != PN_B200_FIXEDPOINT)
+    return fail(PN_B200_ERR_ARGUMENT, "unknown strategy");
+  if (d->correction != PN_B200_TS0 && d->correction != PN_B200_TS1)
+    return fail(PN_B200_ERR_ARGUMENT, "unknown correction");
+  if (d->calibration != PN_B200_CALIB_NONE && d->calibration != PN_B200_CALIB_DYNAMIC)
+    return fail(PN_B200_ERR_ARGUMENT, "unknown calibration");
+  if ((d->flags & PN_B200_FLAG_RECORD) && d->strategy != PN_B200_FILTER)
+    return fail(PN_B200_ERR_UNSUPPORTED, "trajectory recording is implemented for the filter strategy");
+  const KernelEntry* k = nullptr;
+  // thread-per-IVP family: isotropic EKF0 (any compiled d) and dense with d == 1
+  bool scalar_ok = (d->factorisation == PN_B200_ISOTROPIC && d->correction == PN_B200_TS0) ||
+                   (d->factorisation == PN_B200_DENSE && d->d == 1) ||
+                   (d->factorisation == PN_B200_BLOCKDIAG && d->d == 1 && d->correction == PN_B200_TS0);
+  if (scalar_ok) k = find_kernel(FAMILY_SCALAR, d->problem, d->nu, d->strategy);
+  if (!k) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "no kernel compiled for problem=%d nu=%d factorisation=%d correction=%d strategy=%d d=%d",
+             d->problem, d->nu, d->factorisation, d->correction, d->strategy, d->d);
+    return fail(PN_B200_ERR_UNSUPPORTED, buf);
+  }
+  if (k->D != d->d || k->Q != d->ode_order) return fail(PN_B200_ERR_ARGUMENT, "d / ode_order do not match the problem");
+  if (d->correction == PN_B200_TS1 && !k->has_jac) return fail(PN_B200_ERR_UNSUPPORTED, "problem has no compiled Jacobian");
+  if (d->num_params < 0 || d->num_params > (k->P > 0 ? k->P : 0)) return fail(PN_B200_ERR_ARGUMENT, "num_params exceeds the problem's parameter count");
+  *out = k;
+  return PN_B200_SUCCESS;
+}
+
+static int make_plan(const pn_b200_desc* d, Plan* p, bool need_device) {
+  int rc = resolve(d, &p->k);
+  if (rc) return rc;
+  p->smem = (size_t)p->k->smem_doubles * p->k->threads * sizeof(double);
+  p->ws_cond = (size_t)d->num_save_at * p->k->slot_doubles * (size_t)d->batch * sizeof(double);
+  if (!need_device) return PN_B200_SUCCESS;
+  int dev = 0;
+  cudaError_t ce = cudaGetDevice(&dev);
+  if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, cudaGetErrorString(ce));
+  cudaDeviceProp prop;
+  ce = cudaGetDeviceProperties(&prop, dev);
+  if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, cudaGetErrorString(ce));
+  p->num_sms = prop.multiProcessorCount;
+  ce = cudaFuncSetAttribute(p->k->solve_func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
+  if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce));
+  int occ = 0;
+  ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, p->k->solve_func, p->k->threads, p->smem);
+  if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, cudaGetErrorString(ce));
+  if (occ < 1) return fail(PN_B200_ERR_CUDA, "kernel does not fit on an SM");
+  p->ctas_per_sm = occ;
+  long long want = (d->batch + p->k->threads - 1) / p->k->threads;
+  long long cap = (long long)occ * p->num_sms;
+  p->grid = (int)(want < cap ? want : cap);
+  if (p->grid < 1) p->grid = 1;
+  return PN_B200_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------------------
+// fp64 peak microbenchmark: 16 independent DFMA chains per thread, fully register resident
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pn_dfma_peak_kernel(double* out, double a, double b, int iters) {
+  double x[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = (double)(threadIdx.x + i) * 1e-3;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) x[i] = fma(x[i], a, b);
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += x[i];
+  if (s == 123456.789) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+}  // namespace pn
+
+using namespace pn;
+
+extern "C" {
+
+const char* pn_b200_last_error(void) { return g_err.c_str(); }
+
+int pn_b200_supported(const pn_b200_desc* desc) {
+  const KernelEntry* k = nullptr;
+  return resolve(desc, &k);
+}
+
+size_t pn_b200_workspace_bytes(const pn_b200_desc* desc) {
+  Plan p;
+  if (make_plan(desc, &p, false)) return 0;
+  return p.ws_ticket + p.ws_cond;
+}
+
+int pn_b200_get_kernel_info(const pn_b200_desc* desc, pn_b200_kernel_info* info) {
+  Plan p;
+  int rc = make_plan(desc, &p, true);
+  if (rc) return rc;
+  cudaFuncAttributes fa;
+  cudaError_t ce = cudaFuncGetAttributes(&fa, p.k->solve_func);
+  if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, cudaGetErrorString(ce));
+  info->threads_per_cta = p.k->threads;
+  info->ctas_per_sm = p.ctas_per_sm;
+  info->num_sms = p.num_sms;
+  info->grid = p.grid;
+  info->registers_per_thread = fa.numRegs;
+  info->static_smem_bytes = (int32_t)fa.sharedSizeBytes;
+  info->dynamic_smem_bytes = (int32_t)p.smem;
+  info->local_bytes_per_thread = (int32_t)fa.localSizeBytes;
+  return PN_B200_SUCCESS;
+}
+
+int pn_b200_solve_save_at(const pn_b200_desc* desc, const double* u0, const double* params,
+                          const double* tol, const double* save_at, const double* output_scale0,
+                          double* u, double* u_std, double* marg_mean, double* marg_chol,
+                          int64_t* n_accepted, int64_t* n_rejected, int32_t* status, double* traj_t,
+                          double* traj_u, double* traj_std, int64_t* traj_len, void* workspace,
+                          size_t workspace_bytes, void* cuda_stream) {
+  Plan p;
+  int rc = make_plan(desc, &p, true);
+  if (rc) return rc;
+  if (desc->batch == 0) return PN_B200_SUCCESS;
+  if (!u0 || !save_at || !u || !u_std || !n_accepted || !n_rejected || !status)
+    return fail(PN_B200_ERR_ARGUMENT, "null required buffer");
+  if (desc->num_params > 0 && !params) return fail(PN_B200_ERR_ARGUMENT, "params is null but num_params > 0");
+  if ((desc->flags & PN_B200_FLAG_RECORD) && (!traj_t || !traj_u || !traj_std || !traj_len || desc->traj_capacity < 2))
+    return fail(PN_B200_ERR_ARGUMENT, "trajectory recording needs traj buffers and traj_capacity >= 2");
+  if (!workspace || workspace_bytes < p.ws_ticket + p.ws_cond) return fail(PN_B200_ERR_WORKSPACE, "workspace too small");
+  cudaStream_t stream = (cudaStream_t)cuda_stream;
+
+  SolveArgs a;
+  memset(&a, 0, sizeof a);
+  a.correction = desc->correction;
+  a.calibration = desc->calibration;
+  a.flags = desc->flags;
+  a.num_params = desc->num_params;
+  a.atol = desc->atol;
+  a.rtol = desc->rtol;
+  a.dt0 = desc->dt0;
+  a.safety = desc->safety;
+  a.factor_min = desc->factor_min;
+  a.factor_max = desc->factor_max;
+  const double nn = (double)(desc->nu + 1);
+  a.pow_i = desc->power_integral / nn;
+  a.pow_p = desc->power_proportional / nn;
+  a.B = desc->batch;
+  a.K = desc->num_save_at;
+  a.max_attempts = desc->max_attempts;
+  a.u0 = u0;
+  a.params = params;
+  a.tol = tol;
+  a.save_at = save_at;
+  a.sigma0 = output_scale0;
+  a.ticket = (unsigned long long*)workspace;
+  a.cond = (double*)((char*)workspace + p.ws_ticket);
+  a.n_accepted = (long long*)n_accepted;
+  a.n_rejected = (long long*)n_rejected;
+  a.status = status;
+  a.traj_t = traj_t;
+  a.traj_u = traj_u;
+  a.traj_std = traj_std;
+  a.traj_cap = desc->traj_capacity;
+  a.traj_len = (long long*)traj_len;
+  prior_lq(desc->nu, a.lq);
+
+  cudaError_t ce = cudaMemsetAsync(workspace, 0, p.ws_ticket, stream);
+  if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, cudaGetErrorString(ce));
+  ce = p.k->launch_solve(a, p.grid, p.smem, stream);
+  if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, std::string("solve kernel launch: ") + cudaGetErrorString(ce));
+
+  SmoothArgs s;
+  s.B = desc->batch;
+  s.K = desc->num_save_at;
+  s.cond = a.cond;
+  s.status = status;
+  s.u = u;
+  s.u_std = u_std;
+  s.marg_mean = marg_mean;
+  s.marg_chol = marg_chol;
+  ce = p.k->launch_smooth(s, stream);
+  if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, std::string("smoothing kernel launch: ") + cudaGetErrorString(ce));
+  return PN_B200_SUCCESS;
+}
+
+int pn_b200_solve_save_at_host(const pn_b200_desc* desc, const double* u0, const double* params,
+                               const double* tol, const double* save_at, const double* output_scale0,
+                               double* u, double* u_std, double* marg_mean, double* marg_chol,
+                               int64_t* n_accepted, int64_t* n_rejected, int32_t* status, double* traj_t,
+                               double* traj_u, double* traj_std, int64_t* traj_len, int device) {
+  cudaError_t ce = cudaSetDevice(device);
+  if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, cudaGetErrorString(ce));
+  const KernelEntry* k = nullptr;
+  int rc = resolve(desc, &k);
+  if (rc) return rc;
+  if (desc->batch == 0) return PN_B200_SUCCESS;
+  const size_t B = (size_t)desc->batch, K = (size_t)desc->num_save_at, d = (size_t)desc->d, n = (size_t)desc->nu + 1;
+  const size_t q = (size_t)desc->ode_order, P = (size_t)desc->num_params;
+  const bool rec = (desc->flags & PN_B200_FLAG_RECORD) != 0;
+  const size_t cap = rec ? (size_t)desc->traj_capacity : 0;
+  struct Buf {
+    void** dev;
+    const void* host_in;
+    void* host_out;
+    size_t bytes;
+  };
+  void *d_u0 = 0, *d_par = 0, *d_tol = 0, *d_save = 0, *d_os = 0, *d_u = 0, *d_std = 0, *d_mm = 0, *d_mc = 0;
+  void *d_nacc = 0, *d_nrej = 0, *d_stat = 0, *d_tt = 0, *d_tu = 0, *d_ts = 0, *d_tl = 0, *d_ws = 0;
+  size_t ws_bytes = pn_b200_workspace_bytes(desc);
+  Buf bufs[] = {
+      {&d_u0, u0, nullptr, B * q * d * 8},
+      {&d_par, P ? params : nullptr, nullptr, P ? B * P * 8 : 0},
+      {&d_tol, tol, nullptr, tol ? B * 2 * 8 : 0},
+      {&d_save, save_at, nullptr, K * 8},
+      {&d_os, output_scale0, nullptr, output_scale0 ? B * 8 : 0},
+      {&d_u, nullptr, u, B * K * d * 8},
+      {&d_std, nullptr, u_std, B * K * d * 8},
+      {&d_mm, nullptr, marg_mean, marg_mean ? B * K * n * d * 8 : 0},
+      {&d_mc, nullptr, marg_chol, marg_chol ? B * K * n * n * 8 : 0},
+      {&d_nacc, nullptr, n_accepted, B * K * 8},
+      {&d_nrej, nullptr, n_rejected, B * 8},
+      {&d_stat, nullptr, status, B * 4},
+      {&d_tt, nullptr, traj_t, rec ? cap * B * 8 : 0},
+      {&d_tu, nullptr, traj_u, rec ? cap * d * B * 8 : 0},
+      {&d_ts, nullptr, traj_std, rec ? cap * B * 8 : 0},
+      {&d_tl, nullptr, traj_len, rec ? B * 8 : 0},
+      {&d_ws, nullptr, nullptr, ws_bytes},
+  };
+  cudaStream_t stream;
+  ce = cudaStreamCreate(&stream);
+  if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, cudaGetErrorString(ce));
+  rc = PN_B200_SUCCESS;
+  for (auto& bf : bufs) {
+    if (!bf.bytes) continue;
+    ce = cudaMallocAsync(bf.dev, bf.bytes, stream);
+    if (ce != cudaSuccess) { rc = fail(PN_B200_ERR_CUDA, std::string("cudaMallocAsync: ") + cudaGetErrorString(ce)); break; }
+    if (bf.host_in) {
+      ce = cudaMemcpyAsync(*bf.dev, bf.host_in, bf.bytes, cudaMemcpyHostToDevice, stream);
+      if (ce != cudaSuccess) { rc = fail(PN_B200_ERR_CUDA, cudaGetErrorString(ce)); break; }
+    }
+  }
+  if (rc == PN_B200_SUCCESS)
+    rc = pn_b200_solve_save_at(desc, (const double*)d_u0, (const double*)d_par, (const double*)d_tol,
+                               (const double*)d_save, (const double*)d_os, (double*)d_u, (double*)d_std,
+                               (double*)d_mm, (double*)d_mc, (int64_t*)d_nacc, (int64_t*)d_nrej,
+                               (int32_t*)d_stat, (double*)d_tt, (double*)d_tu, (double*)d_ts, (int64_t*)d_tl,
+                               d_ws, ws_bytes, stream);
+  if (rc == PN_B200_SUCCESS) {
+    for (auto& bf : bufs) {
+      if (!bf.bytes || !bf.host_out) continue;
+      ce = cudaMemcpyAsync(bf.host_out, *bf.dev, bf.bytes, cudaMemcpyDeviceToHost, stream);
+      if (ce != cudaSuccess) { rc = fail(PN_B200_ERR_CUDA, cudaGetErrorString(ce)); break; }
+    }
+  }
+  ce = cudaStreamSynchronize(stream);
+  if (ce != cudaSuccess && rc == PN_B200_SUCCESS) rc = fail(PN_B200_ERR_CUDA, std::string("stream sync: ") + cudaGetErrorString(ce));
+  for (auto& bf : bufs)
+    if (*bf.dev) cudaFreeAsync(*bf.dev, stream);
+  cudaStreamSynchronize(stream);
+  cudaStreamDestroy(stream);
+  return rc;
+}
+
+int pn_b200_measure_fp64_peak(double* tflops, void* cuda_stream) {
+  cudaStream_t stream = (cudaStream_t)cuda_stream;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceProp prop;
+  cudaError_t ce = cudaGetDeviceProperties(&prop, dev);
+  if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, cudaGetErrorString(ce));
+  const int threads = 256, ctas = prop.multiProcessorCount * 8, iters = 4096;
+  double* out = nullptr;
+  ce = cudaMalloc(&out, (size_t)threads * ctas * sizeof(double));
+  if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, cudaGetErrorString(ce));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0, stream);
+    pn_dfma_peak_kernel<<<ctas, threads, 0, stream>>>(out, 0.999999, 1e-9, iters);
+    cudaEventRecord(e1, stream);
+    ce = cudaEventSynchronize(e1);
+    if (ce != cudaSuccess) break;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    double flops = 2.0 * 16 * 8 * (double)iters * threads * (double)ctas;
+    double tf = flops / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, cudaGetErrorString(ce));
+  *tflops = best;
+  return PN_B200_SUCCESS;
+}
+
+}  // extern "C"

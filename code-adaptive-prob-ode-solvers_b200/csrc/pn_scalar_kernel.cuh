@@ -1,0 +1,745 @@
+// pn_scalar_kernel.cuh -- thread-per-IVP persistent solver kernel (sm_100a, fp64).
+//
+// One CUDA thread owns one IVP of the ensemble and runs the whole adaptive time loop of
+// probdiffeq's `ivpsolve.solve_adaptive_save_at` (called at
+// src/odecheckpts/ivpsolvers.py:71-77, experiments/4_brusselator/run.py:122-129,
+// experiments/5_vs_interpolation/measure.py:66-68) for state-space models whose square-root
+// factors are n x n (n = nu+1):
+//   * isotropic factorisation (impl.select("isotropic"), ivpsolvers.py:32-33) with EKF0
+//     (correction_ts0) for small ODE dimension D (mean n x D in registers), and
+//   * dense factorisation with D == 1 (experiments/1_van_der_pol/vdp.py:61-66) with EKF0/EKF1.
+// The algorithm is SURVEY.md Appendix A: IWP prior in preconditioned coordinates (A.1),
+// one attempted step = predict mean -> linearise -> calibrate + local error -> predict
+// sqrt-covariance by Householder QR of the stacked factors (fixed-point strategy: 2n x 2n block
+// QR + triangular solve -> backward conditional, merged into the running conditional) ->
+// sqrt correction -> scaled error norm -> PI controller (A.3, A.4); checkpoints by
+// interpolation with an identity-reset backward model (A.5).
+//
+// Design (B200-first, not a translation of the JAX control flow):
+//   * All lanes of a warp always execute the SAME straight-line "uber step": a lane is either
+//     attempting a step (MODE_STEP) or doing one of the two extra predictions a checkpoint
+//     needs (MODE_INTERP_A: previous state -> checkpoint, MODE_INTERP_B: checkpoint -> accepted
+//     state).  Accept/reject and checkpoint handling only change which results a lane commits,
+//     so per-member step control costs predicated moves, not divergent code.
+//   * Hidden state (mean, Cholesky factor) lives in registers; the running backward conditional
+//     (G, g, Lam) and the accepted-but-uncommitted state of a lane that is interpolating are parked
+//     in shared memory ([element][thread], conflict free).
+//   * Lanes pull members from a global atomic ticket, so differing step counts (tolerance
+//     sweeps) never idle a lane while work remains.
+//   * HBM traffic: inputs once per member; per checkpoint one backward conditional
+//     ([checkpoint][element][member], member-minor so a warp's stores coalesce).
+//   * The O(K) backward marginalisation (stats.markov_marginals(reverse=True),
+//     ivpsolvers.py:80-81) runs as a second, fully convergent kernel (pn_smooth_kernel).
+//
+// Arithmetic order follows oracle/pn_solver.c exactly, skipping structural zeros only (which is
+// exact), so results are comparable bit for bit.
+#pragma once
+#include "pn_math.cuh"
+#include "pn_problems.cuh"
+
+namespace pn {
+
+enum : int { MODE_STEP = 0, MODE_INTERP_A = 1, MODE_INTERP_B = 2 };
+enum : int { FLAG_FIXED_GRID = 1, FLAG_RECORD = 2 };
+
+struct SolveArgs {
+  int32_t correction;   // 0 ts0, 1 ts1 (D == 1 only)
+  int32_t calibration;  // 0 none, 1 dynamic
+  int32_t flags;
+  int32_t num_params;
+  double atol, rtol, dt0;
+  double safety, factor_min, factor_max, pow_i, pow_p;  // pow_* already divided by n
+  long long B, K, max_attempts;
+  const double* u0;       // [B][Q*D]
+  const double* params;   // [B][P]
+  const double* tol;      // nullable [B][2]
+  const double* save_at;  // [K]
+  const double* sigma0;   // nullable [B]
+  double* cond;           // workspace [K][E][B], slot 0 = terminal state
+  long long* n_accepted;  // [B][K]
+  long long* n_rejected;  // [B]
+  int32_t* status;        // [B]
+  unsigned long long* ticket;
+  // optional trajectory recording (solve_adaptive_save_every_step, vdp.py:77-79)
+  double* traj_t;    // [cap][B]
+  double* traj_u;    // [cap][D][B]
+  double* traj_std;  // [cap][B]   (isotropic: one std for all dimensions)
+  long long traj_cap;
+  long long* traj_len;  // [B]
+  // Prior constant: lower Cholesky factor of the flipped Hilbert matrix, row-major
+  // n x n, computed by the host (pn_capi.cu).  Kernel parameters live in the constant bank, so
+  // DFMA reads these entries as immediate constant operands.
+  double lq[100];
+};
+
+template <int N>
+struct Binom {
+  // flipped Pascal matrix A1[i][j] = C(nu-i, nu-j)
+  __host__ __device__ static constexpr double at(int i, int j) {
+    int a = N - 1 - i, b = N - 1 - j;
+    if (b < 0 || b > a) return 0.0;
+    double c = 1.0;
+    for (int k = 1; k <= b; ++k) c = c * (double)(a - b + k) / (double)k;
+    return c;
+  }
+};
+
+__host__ __device__ constexpr double factorial(int k) {
+  double f = 1.0;
+  for (int i = 2; i <= k; ++i) f *= (double)i;
+  return f;
+}
+
+// number of doubles one backward conditional / one marginal occupies
+template <int N, int D>
+struct Layout {
+  static constexpr int NT = N * (N + 1) / 2;
+  static constexpr int BW = N * N + N * D + NT;   // G (full), g, Lam (lower, packed)
+  static constexpr int MARG = N * D + NT;         // mean, chol (lower, packed)
+  static constexpr int PEND = MARG + 2;           // + t1, sigma1
+  static constexpr int SLOT_FIX = BW + MARG;      // fixed-point slot: cond (+ terminal marginal in slot 0)
+  static constexpr int SLOT_FILT = MARG;          // filter slot: the marginal itself
+  __host__ __device__ static constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }  // j <= i
+};
+
+template <class Prob, int NU, int STRAT, int THREADS>
+__global__ void __launch_bounds__(THREADS) pn_scalar_kernel(const __grid_constant__ SolveArgs a) {
+  constexpr int N = NU + 1, D = Prob::D, Q = Prob::Q, P = (Prob::P > 0 ? Prob::P : 1);
+  using Lay = Layout<N, D>;
+  constexpr bool FIX = (STRAT == 1);
+  constexpr int SLOT = FIX ? Lay::SLOT_FIX : Lay::SLOT_FILT;
+  constexpr double TIME_EPS = 10.0 * 2.220446049250313e-16;
+
+  extern __shared__ double smem[];
+  // [element][thread]
+  double* s_bw = smem;                                       // BW * THREADS (fixed-point only)
+  double* s_pend = smem + (FIX ? Lay::BW : 0) * THREADS;     // PEND * THREADS
+  const int tid = threadIdx.x;
+#define SBW(e) s_bw[(e) * THREADS + tid]
+#define SPEND(e) s_pend[(e) * THREADS + tid]
+  constexpr int OFF_G = 0, OFF_g = N * N, OFF_LAM = N * N + N * D;
+
+  const double* LQ = a.lq;
+  const double sqrt_d = dsqrt((double)D);
+
+  // ---- per-lane persistent state --------------------------------------------------------
+  bool have = false, exhausted = false;
+  long long b = 0;
+  double t = 0.0, dt_next = 0.0, e_prev = 1.0, sigma_state = 1.0, sigma0 = 1.0;
+  double atol = a.atol, rtol = a.rtol;
+  double par[P];
+  double m[N][D];
+  double L[N][N];  // lower triangle used
+  int mode = MODE_STEP;
+  long long k_next = 1, n_acc = 0, n_rej = 0, n_att = 0;
+
+  for (;;) {
+    // ---- fetch a member ----------------------------------------------------------------
+    if (!have && !exhausted) {
+      unsigned long long tk = atomicAdd(a.ticket, 1ULL);
+      if (tk < (unsigned long long)a.B) {
+        b = (long long)tk;
+        have = true;
+        double u0[Q * D];
+#pragma unroll
+        for (int i = 0; i < Q * D; ++i) u0[i] = a.u0[b * (Q * D) + i];
+#pragma unroll
+        for (int i = 0; i < P; ++i) par[i] = (i < a.num_params) ? a.params[b * a.num_params + i] : 0.0;
+        atol = a.tol ? a.tol[2 * b] : a.atol;
+        rtol = a.tol ? a.tol[2 * b + 1] : a.rtol;
+        sigma0 = a.sigma0 ? a.sigma0[b] : 1.0;
+        taylor_init<Prob, NU>(u0, par, m);
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+          for (int j = 0; j <= i; ++j) L[i][j] = 0.0;
+        if (FIX) {
+#pragma unroll
+          for (int e = 0; e < Lay::BW; ++e) SBW(e) = 0.0;
+#pragma unroll
+          for (int i = 0; i < N; ++i) SBW(OFF_G + i * N + i) = 1.0;
+        }
+        t = a.save_at[0];
+        dt_next = a.dt0;
+        e_prev = 1.0;
+        sigma_state = sigma0;
+        mode = MODE_STEP;
+        k_next = 1;
+        n_acc = n_rej = n_att = 0;
+        a.n_accepted[b * a.K] = 0;
+        if (a.flags & FLAG_RECORD) {
+          a.traj_t[b] = t;
+#pragma unroll
+          for (int c = 0; c < D; ++c) a.traj_u[(long long)c * a.B + b] = m[0][c];
+          a.traj_std[b] = 0.0;
+        }
+        if (!FIX) {
+          // filter: slot 0 holds the initial marginal
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+#pragma unroll
+            for (int c = 0; c < D; ++c) a.cond[(long long)(i * D + c) * a.B + b] = m[i][c];
+#pragma unroll
+            for (int j = 0; j <= i; ++j) a.cond[(long long)(N * D + Lay::tri(i, j)) * a.B + b] = 0.0;
+          }
+        }
+      } else {
+        exhausted = true;
+      }
+    }
+    if (!__any_sync(0xffffffffu, have)) break;
+    if (!have) continue;  // idle lane; the warp-level vote above keeps the loop convergent
+
+    // ---- choose this iteration's prediction --------------------------------------------
+    double t_ck = a.save_at[k_next < a.K ? k_next : a.K - 1];
+    double dt, sigma_given;
+    if (mode == MODE_STEP) {
+      dt = (a.flags & FLAG_FIXED_GRID) ? (t_ck - t) : dt_next;
+      sigma_given = sigma0;
+    } else if (mode == MODE_INTERP_A) {
+      dt = t_ck - t;
+      sigma_given = SPEND(1);
+    } else {
+      dt = SPEND(0) - t;
+      sigma_given = SPEND(1);
+    }
+
+    // ==================== uber step (straight-line, identical for all lanes) ============
+    // A.1 preconditioner
+    double p[N], pinv[N];
+    {
+      double adt = fabs(dt);
+      double sq = dsqrt(adt);
+      double isq = rcp(sq), idt = rcp(adt);
+      double dtp = 1.0, idtp = 1.0;
+#pragma unroll
+      for (int k = 0; k <= NU; ++k) {
+        const int i = NU - k;
+        p[i] = (sq * dtp) * (1.0 / factorial(k));
+        pinv[i] = (isq * idtp) * factorial(k);
+        dtp *= adt;
+        idtp *= idt;
+      }
+    }
+    // predicted mean
+    double m_p[N][D], m_ext_p[N][D], m_ext[N][D];
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int c = 0; c < D; ++c) m_p[i][c] = pinv[i] * m[i][c];
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        double acc = m_p[i][c];
+#pragma unroll
+        for (int j = i + 1; j < N; ++j) acc = fma(Binom<N>::at(i, j), m_p[j][c], acc);
+        m_ext_p[i][c] = acc;
+        m_ext[i][c] = p[i] * acc;
+      }
+    // linearise at the predicted mean
+    double z[D], h[Q + 1];
+    {
+      double uarg[Q * D], f[D];
+#pragma unroll
+      for (int k = 0; k < Q; ++k)
+#pragma unroll
+        for (int c = 0; c < D; ++c) uarg[k * D + c] = m_ext[k][c];
+      Prob::vf(uarg, par, f);
+#pragma unroll
+      for (int c = 0; c < D; ++c) z[c] = m_ext[Q][c] - f[c];
+#pragma unroll
+      for (int k = 0; k < Q; ++k) h[k] = 0.0;
+      h[Q] = 1.0;
+      if (D == 1 && Prob::HAS_JAC && a.correction == 1) {
+        double J[Q * D * D];
+        Prob::jac(uarg, par, J);
+#pragma unroll
+        for (int k = 0; k < Q; ++k) h[k] = -J[k];
+      }
+    }
+    // local calibration + error estimate from the process noise
+    double err, sigma;
+    {
+      double s2 = 0.0;
+#pragma unroll
+      for (int j = 0; j <= Q; ++j) {
+        double acc = 0.0;
+#pragma unroll
+        for (int i = j; i <= Q; ++i) acc = fma(h[i] * p[i], LQ[i * N + j], acc);
+        s2 = fma(acc, acc, s2);
+      }
+      double s = dsqrt(s2);
+      double zz = 0.0;
+#pragma unroll
+      for (int c = 0; c < D; ++c) zz = fma(z[c], z[c], zz);
+      double sigma_hat = (dsqrt(zz) / s) / sqrt_d;
+      err = (fabs(dt) * sigma_hat) * s;
+      sigma = (mode == MODE_STEP) ? ((a.calibration == 1) ? sigma_hat : sigma_given) : sigma_given;
+    }
+    // predict the square-root covariance
+    double L_ext[N][N];         // lower
+    double Gn[N][N], gn[N][D];  // new conditional (un-preconditioned); Lam_n lower
+    double Ln[N][N];
+    {
+      double L_p[N][N];  // lower
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) L_p[i][j] = pinv[i] * L[i][j];
+      // BL[i][j] = (A L_p)[j][i]
+      double BL[N][N];
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          const int k0 = (i > j) ? i : j;
+          double acc = (k0 == i) ? L_p[i][j] : Binom<N>::at(i, k0) * L_p[k0][j];
+#pragma unroll
+          for (int k = k0 + 1; k < N; ++k) acc = fma(Binom<N>::at(i, k), L_p[k][j], acc);
+          BL[j][i] = acc;
+        }
+      // top-left block rows: TL[j][c] = sigma * LQ[c][j] (c >= j), materialised when row j is used
+      double RY[N][N];   // upper
+      double R12[N][N];  // full (fixed-point)
+      double BR[N][N];   // bottom-right block, starts as L_p^T (upper), fills in (fixed-point)
+      if (FIX) {
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+          for (int c = 0; c < N; ++c) BR[i][c] = (i <= c) ? L_p[c][i] : 0.0;
+      }
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        double sigma2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) sigma2 = fma(BL[i][j], BL[i][j], sigma2);
+        const double alpha = sigma * LQ[j * N + j];
+        Reflector rf = make_reflector(alpha, sigma2);
+        RY[j][j] = rf.beta;
+        // left block columns c > j
+#pragma unroll
+        for (int c = j + 1; c < N; ++c) {
+          double top = sigma * LQ[c * N + j];
+          double w = rf.v0 * top;
+#pragma unroll
+          for (int i = 0; i < N; ++i) w = fma(BL[i][j], BL[i][c], w);
+          double f = w * rf.g;
+          RY[j][c] = fma(-f, rf.v0, top);
+#pragma unroll
+          for (int i = 0; i < N; ++i) BL[i][c] = fma(-f, BL[i][j], BL[i][c]);
+        }
+        if (FIX) {
+          // right block columns: top entry starts at 0
+#pragma unroll
+          for (int c = 0; c < N; ++c) {
+            double w = rf.v0 * 0.0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+              if (j == 0 && i > c) continue;  // still structurally zero
+              w = fma(BL[i][j], BR[i][c], w);
+            }
+            double f = w * rf.g;
+            R12[j][c] = fma(-f, rf.v0, 0.0);
+#pragma unroll
+            for (int i = 0; i < N; ++i) BR[i][c] = fma(-f, BL[i][j], BR[i][c]);
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) L_ext[i][j] = p[i] * RY[j][i];
+      if (FIX) {
+        // phase 2: QR of the (now full) bottom-right block
+#pragma unroll
+        for (int j = 0; j < N - 1; ++j) {
+          double sigma2 = 0.0;
+#pragma unroll
+          for (int i = j + 1; i < N; ++i) sigma2 = fma(BR[i][j], BR[i][j], sigma2);
+          Reflector rf = make_reflector(BR[j][j], sigma2);
+#pragma unroll
+          for (int c = j + 1; c < N; ++c) {
+            double w = rf.v0 * BR[j][c];
+#pragma unroll
+            for (int i = j + 1; i < N; ++i) w = fma(BR[i][j], BR[i][c], w);
+            double f = w * rf.g;
+            BR[j][c] = fma(-f, rf.v0, BR[j][c]);
+#pragma unroll
+            for (int i = j + 1; i < N; ++i) BR[i][c] = fma(-f, BR[i][j], BR[i][c]);
+          }
+          BR[j][j] = rf.beta;
+        }
+        // X = RY^{-1} R12 (back substitution); G_p = X^T
+        double X[N][N];
+#pragma unroll
+        for (int i = N - 1; i >= 0; --i) {
+          double inv = rcp(RY[i][i]);
+#pragma unroll
+          for (int c = 0; c < N; ++c) {
+            double acc = R12[i][c];
+#pragma unroll
+            for (int k = i + 1; k < N; ++k) acc = fma(-RY[i][k], X[k][c], acc);
+            X[i][c] = acc * inv;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+#pragma unroll
+          for (int c = 0; c < D; ++c) {
+            double acc = m_p[i][c];
+#pragma unroll
+            for (int k = 0; k < N; ++k) acc = fma(-X[k][i], m_ext_p[k][c], acc);
+            gn[i][c] = p[i] * acc;
+          }
+#pragma unroll
+          for (int j = 0; j < N; ++j) Gn[i][j] = (p[i] * X[j][i]) * pinv[j];
+#pragma unroll
+          for (int j = 0; j <= i; ++j) Ln[i][j] = p[i] * BR[j][i];
+        }
+      }
+    }
+    // merge with the running conditional (A.4); running conditional lives in shared memory
+    double Gm[N][N], gm[N][D], Lm[N][N];
+    if (FIX) {
+      double G1[N][N];
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) G1[i][j] = SBW(OFF_G + i * N + j);
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          double acc = G1[i][0] * Gn[0][j];
+#pragma unroll
+          for (int k = 1; k < N; ++k) acc = fma(G1[i][k], Gn[k][j], acc);
+          Gm[i][j] = acc;
+        }
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          double acc = SBW(OFF_g + i * D + c);
+#pragma unroll
+          for (int k = 0; k < N; ++k) acc = fma(G1[i][k], gn[k][c], acc);
+          gm[i][c] = acc;
+        }
+      }
+      // T = G1 Lam_n ; M = [T^T ; Lam_run^T]
+      double Mt[N][N];  // Mt[i][j] = T[j][i]
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          double acc = G1[i][j] * Ln[j][j];
+#pragma unroll
+          for (int k = j + 1; k < N; ++k) acc = fma(G1[i][k], Ln[k][j], acc);
+          Mt[j][i] = acc;
+        }
+      double Mb[N][N];  // Mb[i][j] = Lam_run[j][i], nonzero for i <= j
+#pragma unroll
+      for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int i = 0; i <= j; ++i) Mb[i][j] = SBW(OFF_LAM + Lay::tri(j, i));
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        double sigma2 = 0.0;
+#pragma unroll
+        for (int i = j + 1; i < N; ++i) sigma2 = fma(Mt[i][j], Mt[i][j], sigma2);
+#pragma unroll
+        for (int i = 0; i <= j; ++i) sigma2 = fma(Mb[i][j], Mb[i][j], sigma2);
+        Reflector rf = make_reflector(Mt[j][j], sigma2);
+#pragma unroll
+        for (int c = j + 1; c < N; ++c) {
+          double w = rf.v0 * Mt[j][c];
+#pragma unroll
+          for (int i = j + 1; i < N; ++i) w = fma(Mt[i][j], Mt[i][c], w);
+#pragma unroll
+          for (int i = 0; i <= j; ++i) w = fma(Mb[i][j], Mb[i][c], w);
+          double f = w * rf.g;
+          Mt[j][c] = fma(-f, rf.v0, Mt[j][c]);
+#pragma unroll
+          for (int i = j + 1; i < N; ++i) Mt[i][c] = fma(-f, Mt[i][j], Mt[i][c]);
+#pragma unroll
+          for (int i = 0; i <= j; ++i) Mb[i][c] = fma(-f, Mb[i][j], Mb[i][c]);
+        }
+        Mt[j][j] = rf.beta;
+      }
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) Lm[i][j] = Mt[j][i];
+    }
+    // correction (noise-free observation, sqrt form)
+    double m_new[N][D], L_new[N][N];
+    double e_norm;
+    {
+      double hL[Q + 1];
+      double S = 0.0;
+#pragma unroll
+      for (int j = 0; j <= Q; ++j) {
+        double acc = 0.0;
+#pragma unroll
+        for (int i = j; i <= Q; ++i) acc = fma(h[i], L_ext[i][j], acc);
+        hL[j] = acc;
+        S = fma(acc, acc, S);
+      }
+      double invS = rcp(S);
+      double gain[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j <= ((i < Q) ? i : Q); ++j) acc = fma(L_ext[i][j], hL[j], acc);
+        gain[i] = acc * invS;
+      }
+      // Mc[j][i] = L_ext[i][j] - hL[j] gain[i]; rows j > Q are untouched rows of L_ext^T
+      double Mc[Q + 1][N];
+#pragma unroll
+      for (int j = 0; j <= Q; ++j)
+#pragma unroll
+        for (int i = 0; i < N; ++i) Mc[j][i] = fma(-hL[j], gain[i], (j <= i) ? L_ext[i][j] : 0.0);
+#pragma unroll
+      for (int c0 = 0; c0 < Q; ++c0) {
+        double sigma2 = 0.0;
+#pragma unroll
+        for (int i = c0 + 1; i <= Q; ++i) sigma2 = fma(Mc[i][c0], Mc[i][c0], sigma2);
+        Reflector rf = make_reflector(Mc[c0][c0], sigma2);
+#pragma unroll
+        for (int c = c0 + 1; c < N; ++c) {
+          double w = rf.v0 * Mc[c0][c];
+#pragma unroll
+          for (int i = c0 + 1; i <= Q; ++i) w = fma(Mc[i][c0], Mc[i][c], w);
+          double f = w * rf.g;
+          Mc[c0][c] = fma(-f, rf.v0, Mc[c0][c]);
+#pragma unroll
+          for (int i = c0 + 1; i <= Q; ++i) Mc[i][c] = fma(-f, Mc[i][c0], Mc[i][c]);
+        }
+        Mc[c0][c0] = rf.beta;
+      }
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) L_new[i][j] = (j <= Q) ? Mc[j][i] : L_ext[i][j];
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int c = 0; c < D; ++c) m_new[i][c] = fma(-gain[i], z[c], m_ext[i][c]);
+      double acc = 0.0;
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        double ratio = err / fma(rtol, fabs(m_new[0][c]), atol);
+        acc = fma(ratio, ratio, acc);
+      }
+      e_norm = dsqrt(acc) / sqrt_d;
+    }
+    // PI controller
+    double fac;
+    {
+      double a1 = det_pow(1.0 / e_norm, a.pow_i);
+      double a2 = det_pow(e_prev / e_norm, a.pow_p);
+      fac = (a.safety * a1) * a2;
+      fac = (fac < a.factor_max) ? fac : a.factor_max;
+      fac = (fac > a.factor_min) ? fac : a.factor_min;
+    }
+    // ==================== per-lane bookkeeping (cheap, may diverge) =====================
+    // helpers -------------------------------------------------------------------------
+    auto ck_time = [&](long long k) { return a.save_at[k < a.K ? k : a.K - 1]; };
+    auto store_cond = [&](double* dst /* element stride a.B */) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) dst[(long long)(OFF_G + i * N + j) * a.B] = Gm[i][j];
+#pragma unroll
+        for (int c = 0; c < D; ++c) dst[(long long)(OFF_g + i * D + c) * a.B] = gm[i][c];
+#pragma unroll
+        for (int j = 0; j <= i; ++j) dst[(long long)(OFF_LAM + Lay::tri(i, j)) * a.B] = Lm[i][j];
+      }
+    };
+    auto store_identity_cond = [&](double* dst) {
+#pragma unroll
+      for (int e = 0; e < Lay::BW; ++e) dst[(long long)e * a.B] = 0.0;
+#pragma unroll
+      for (int i = 0; i < N; ++i) dst[(long long)(OFF_G + i * N + i) * a.B] = 1.0;
+    };
+    auto bw_commit = [&]() {  // running conditional <- merged result
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) SBW(OFF_G + i * N + j) = Gm[i][j];
+#pragma unroll
+        for (int c = 0; c < D; ++c) SBW(OFF_g + i * D + c) = gm[i][c];
+#pragma unroll
+        for (int j = 0; j <= i; ++j) SBW(OFF_LAM + Lay::tri(i, j)) = Lm[i][j];
+      }
+    };
+    auto bw_reset = [&]() {  // running conditional <- identity (A.2)
+#pragma unroll
+      for (int e = 0; e < Lay::BW; ++e) SBW(e) = 0.0;
+#pragma unroll
+      for (int i = 0; i < N; ++i) SBW(OFF_G + i * N + i) = 1.0;
+    };
+    auto store_marg = [&](double* dst, const double (&mm)[N][D], const double (&LL)[N][N]) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) dst[(long long)(i * D + c) * a.B] = mm[i][c];
+#pragma unroll
+        for (int j = 0; j <= i; ++j) dst[(long long)(N * D + Lay::tri(i, j)) * a.B] = LL[i][j];
+      }
+    };
+    auto record = [&](double tt, const double (&mm)[N][D], const double (&LL)[N][N]) {
+      if ((a.flags & FLAG_RECORD) && n_acc < a.traj_cap) {
+        a.traj_t[n_acc * a.B + b] = tt;
+#pragma unroll
+        for (int c = 0; c < D; ++c) a.traj_u[(n_acc * D + c) * a.B + b] = mm[0][c];
+        a.traj_std[n_acc * a.B + b] = dsqrt(fma(LL[0][0], LL[0][0], 0.0));
+      }
+    };
+    // exact hits on checkpoints by the committed state (m, L, running conditional): emit, reset
+    auto resolve_hits = [&](bool& fin) {
+      while (k_next < a.K && !(t + TIME_EPS < ck_time(k_next))) {
+        double* slot = a.cond + (k_next * SLOT) * a.B + b;
+        if (FIX) {
+#pragma unroll
+          for (int e = 0; e < Lay::BW; ++e) slot[(long long)e * a.B] = SBW(e);
+          if (k_next == a.K - 1) {
+            store_identity_cond(a.cond + b);
+            store_marg(a.cond + (long long)Lay::BW * a.B + b, m, L);
+          }
+          bw_reset();
+        } else {
+          store_marg(slot, m, L);
+        }
+        a.n_accepted[b * a.K + k_next] = n_acc;
+        k_next += 1;
+      }
+      if (k_next >= a.K) fin = true;
+    };
+    auto commit_pending = [&]() {
+      t = SPEND(0);
+      sigma_state = SPEND(1);
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) m[i][c] = SPEND(2 + i * D + c);
+#pragma unroll
+        for (int j = 0; j <= i; ++j) L[i][j] = SPEND(2 + N * D + Lay::tri(i, j));
+      }
+    };
+    // after a checkpoint was emitted while the accepted state waits in s_pend
+    auto after_checkpoint = [&](bool& fin) {
+      const double t1 = SPEND(0);
+      if (k_next < a.K && t1 > ck_time(k_next) + TIME_EPS) {
+        mode = MODE_INTERP_A;  // the next checkpoint lies inside the same step
+      } else {
+        commit_pending();
+        if (FIX) bw_commit();
+        mode = MODE_STEP;
+        resolve_hits(fin);
+      }
+    };
+
+    bool finished = false;
+    int st = 0;
+    const bool fixed_grid = (a.flags & FLAG_FIXED_GRID) != 0;
+    if (mode == MODE_STEP) {
+      n_att += 1;
+      if (e_norm != e_norm && !fixed_grid) {
+        finished = true;
+        st = 1;
+      } else {
+        dt_next = fac * dt;
+        if (e_norm <= 1.0 || fixed_grid) {
+          if (!fixed_grid) e_prev = e_norm;
+          n_acc += 1;
+          const double t1 = fixed_grid ? t_ck : (t + dt);
+          const bool overshoot = (k_next < a.K) && (t1 > t_ck + TIME_EPS);
+          if (overshoot) {
+            // keep the accepted state aside; interpolate from the (unchanged) previous state
+            SPEND(0) = t1;
+            SPEND(1) = sigma;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+#pragma unroll
+              for (int c = 0; c < D; ++c) SPEND(2 + i * D + c) = m_new[i][c];
+#pragma unroll
+              for (int j = 0; j <= i; ++j) SPEND(2 + N * D + Lay::tri(i, j)) = L_new[i][j];
+            }
+            mode = MODE_INTERP_A;
+          } else {
+            t = t1;
+            sigma_state = sigma;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+#pragma unroll
+              for (int c = 0; c < D; ++c) m[i][c] = m_new[i][c];
+#pragma unroll
+              for (int j = 0; j <= i; ++j) L[i][j] = L_new[i][j];
+            }
+            if (FIX) bw_commit();
+            record(t1, m_new, L_new);
+            resolve_hits(finished);
+          }
+        } else {
+          n_rej += 1;
+        }
+        if (!finished && mode == MODE_STEP && a.max_attempts > 0 && n_att >= a.max_attempts) {
+          finished = true;
+          st = 2;
+        }
+      }
+    } else if (mode == MODE_INTERP_A) {
+      // prediction "previous state -> checkpoint": fixed-point emits the merged conditional
+      // "t_c -> previous checkpoint" and continues from (t_c, m_t, L_t, identity); the filter emits
+      // the extrapolated marginal.
+      double* slot = a.cond + (k_next * SLOT) * a.B + b;
+      if (FIX) {
+        store_cond(slot);
+        bw_reset();
+      } else {
+        store_marg(slot, m_ext, L_ext);
+        record(t_ck, m_ext, L_ext);
+      }
+      t = t_ck;
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) m[i][c] = m_ext[i][c];
+#pragma unroll
+        for (int j = 0; j <= i; ++j) L[i][j] = L_ext[i][j];
+      }
+      a.n_accepted[b * a.K + k_next] = n_acc;
+      if (FIX) {
+        mode = MODE_INTERP_B;
+      } else {
+        k_next += 1;
+        after_checkpoint(finished);
+      }
+    } else {
+      // MODE_INTERP_B (fixed-point): the merged result (running conditional was the identity) is
+      // the conditional "accepted state -> checkpoint"; it becomes the accepted state's backward
+      // model.  At the last checkpoint the terminal marginal marginalise((m1, L1), bw_1t) is
+      // left to the smoothing kernel: store its two ingredients in slot 0.
+      if (k_next == a.K - 1) {
+        store_cond(a.cond + b);
+#pragma unroll
+        for (int e = 0; e < Lay::MARG; ++e) a.cond[(long long)(Lay::BW + e) * a.B + b] = SPEND(2 + e);
+      }
+      k_next += 1;
+      after_checkpoint(finished);
+    }
+    if (finished) {
+      a.n_rejected[b] = n_rej;
+      a.status[b] = st;
+      if (st != 0)
+        for (long long kk = k_next; kk < a.K; ++kk) a.n_accepted[b * a.K + kk] = n_acc;
+      if (a.flags & FLAG_RECORD) a.traj_len[b] = (n_acc + 1 < a.traj_cap) ? (n_acc + 1) : a.traj_cap;
+      have = false;
+    }
+  }
+#undef SBW
+#undef SPEND
+  (void)sigma_state;
+}
+
+}  // namespace pn

@@ -1,0 +1,142 @@
+// pn_smooth_kernel.cuh -- backward marginalisation over the K checkpoints (sm_100a, fp64).
+//
+// Reference: stats.markov_select_terminal + stats.markov_marginals(reverse=True)
+// (src/odecheckpts/ivpsolvers.py:80-81) followed by the QOI selection
+// (impl.hidden_model.qoi_from_sample, ivpsolvers.py:89); SURVEY.md App. A.4/A.6:
+//   rv_{K-1} = terminal marginal;  rv_{k-1} = ( G_k m_k + g_k , R(QR([ (G_k L_k)^T ; Lam_k^T ]))^T ).
+// One thread per member, K-1 sequential marginalisations, all lanes convergent; the
+// conditionals are read member-minor ([checkpoint][element][member]) so every load coalesces.
+// Filter strategy: the stored marginals are the result; this kernel only gathers them.
+#pragma once
+#include "pn_scalar_kernel.cuh"
+
+namespace pn {
+
+struct SmoothArgs {
+  long long B, K;
+  const double* cond;  // [K][SLOT][B]
+  const int32_t* status;
+  double* u;           // [B][K][D]
+  double* u_std;       // [B][K][D]
+  double* marg_mean;   // nullable [B][K][N][D]
+  double* marg_chol;   // nullable [B][K][N][N] (lower triangular, dense storage)
+};
+
+// (m, L) <- marginalise((m, L), (G, g, Lam)); cond read from global memory (stride B)
+template <int N, int D>
+PN_DEV void marginalise_from_global(double (&m)[N][D], double (&L)[N][N], const double* c, long long B) {
+  using Lay = Layout<N, D>;
+  constexpr int OFF_G = 0, OFF_g = N * N, OFF_LAM = N * N + N * D;
+  double G[N][N];
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j < N; ++j) G[i][j] = c[(long long)(OFF_G + i * N + j) * B];
+  double mo[N][D];
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int cc = 0; cc < D; ++cc) {
+      double acc = c[(long long)(OFF_g + i * D + cc) * B];
+#pragma unroll
+      for (int k = 0; k < N; ++k) acc = fma(G[i][k], m[k][cc], acc);
+      mo[i][cc] = acc;
+    }
+  double Mt[N][N], Mb[N][N];
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      double acc = G[i][j] * L[j][j];
+#pragma unroll
+      for (int k = j + 1; k < N; ++k) acc = fma(G[i][k], L[k][j], acc);
+      Mt[j][i] = acc;
+    }
+#pragma unroll
+  for (int j = 0; j < N; ++j)
+#pragma unroll
+    for (int i = 0; i <= j; ++i) Mb[i][j] = c[(long long)(OFF_LAM + Lay::tri(j, i)) * B];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    double sigma2 = 0.0;
+#pragma unroll
+    for (int i = j + 1; i < N; ++i) sigma2 = fma(Mt[i][j], Mt[i][j], sigma2);
+#pragma unroll
+    for (int i = 0; i <= j; ++i) sigma2 = fma(Mb[i][j], Mb[i][j], sigma2);
+    Reflector rf = make_reflector(Mt[j][j], sigma2);
+#pragma unroll
+    for (int cc = j + 1; cc < N; ++cc) {
+      double w = rf.v0 * Mt[j][cc];
+#pragma unroll
+      for (int i = j + 1; i < N; ++i) w = fma(Mt[i][j], Mt[i][cc], w);
+#pragma unroll
+      for (int i = 0; i <= j; ++i) w = fma(Mb[i][j], Mb[i][cc], w);
+      double f = w * rf.g;
+      Mt[j][cc] = fma(-f, rf.v0, Mt[j][cc]);
+#pragma unroll
+      for (int i = j + 1; i < N; ++i) Mt[i][cc] = fma(-f, Mt[i][j], Mt[i][cc]);
+#pragma unroll
+      for (int i = 0; i <= j; ++i) Mb[i][cc] = fma(-f, Mb[i][j], Mb[i][cc]);
+    }
+    Mt[j][j] = rf.beta;
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+#pragma unroll
+    for (int cc = 0; cc < D; ++cc) m[i][cc] = mo[i][cc];
+#pragma unroll
+    for (int j = 0; j <= i; ++j) L[i][j] = Mt[j][i];
+  }
+}
+
+template <int N, int D, int STRAT>
+__global__ void __launch_bounds__(128) pn_smooth_kernel(const SmoothArgs a) {
+  using Lay = Layout<N, D>;
+  constexpr bool FIX = (STRAT == 1);
+  constexpr int SLOT = FIX ? Lay::SLOT_FIX : Lay::SLOT_FILT;
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.B) return;
+  const bool ok = (a.status[b] == 0);
+  double m[N][D], L[N][N];
+  auto load_marg = [&](const double* src) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+#pragma unroll
+      for (int c = 0; c < D; ++c) m[i][c] = src[(long long)(i * D + c) * a.B];
+#pragma unroll
+      for (int j = 0; j <= i; ++j) L[i][j] = src[(long long)(N * D + Lay::tri(i, j)) * a.B];
+    }
+  };
+  if (FIX) {
+    // terminal marginal = marginalise((m1, L1), bw_1t), both stored in slot 0
+    load_marg(a.cond + (long long)Lay::BW * a.B + b);
+    marginalise_from_global<N, D>(m, L, a.cond + b, a.B);
+  }
+  const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+  for (long long k = a.K - 1; k >= 0; --k) {
+    if (!FIX) load_marg(a.cond + (k * SLOT) * a.B + b);
+    const double sd = dsqrt(fma(L[0][0], L[0][0], 0.0));
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      a.u[(b * a.K + k) * D + c] = ok ? m[0][c] : nanv;
+      a.u_std[(b * a.K + k) * D + c] = ok ? sd : nanv;
+    }
+    if (a.marg_mean) {
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int c = 0; c < D; ++c) a.marg_mean[((b * a.K + k) * N + i) * D + c] = ok ? m[i][c] : nanv;
+    }
+    if (a.marg_chol) {
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+          a.marg_chol[((b * a.K + k) * N + i) * N + j] = ok ? ((j <= i) ? L[i][j] : 0.0) : nanv;
+    }
+    if (k == 0) break;
+    if (FIX) marginalise_from_global<N, D>(m, L, a.cond + (k * SLOT) * a.B + b, a.B);
+  }
+}
+
+}  // namespace pn

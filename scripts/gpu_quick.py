@@ -1,0 +1,26 @@
+"""Quick GPU sanity + timing of the headline ensemble (not the bench)."""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "code-adaptive-prob-ode-solvers_b200")); sys.path.insert(0, ROOT)
+import numpy as np, torch
+from odecheckpts_b200 import _cabi
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
+K = 50
+rng = np.random.default_rng(0)
+u0 = np.stack([2.0 + 0.5 * rng.uniform(-1, 1, B), 0.5 * rng.uniform(-1, 1, B)], 1).reshape(B, 2, 1)
+desc = _cabi.Desc(5, 1, 4, 2, 2, 1, 1, 1, 1e-6, 1e-6, 0.01, 0.95, 0.2, 10.0, 0.3, 0.4, B, K, 0, 1, 0, 0)
+print("kernel info", _cabi.kernel_info(desc))
+print("fp64 peak TF", _cabi.measure_fp64_peak())
+dev = torch.device("cuda:0")
+u0_d = torch.as_tensor(u0, device=dev); par = torch.full((B, 1), 1e3, dtype=torch.float64, device=dev)
+save = torch.linspace(0, 6.3, K, dtype=torch.float64, device=dev)
+out = None
+for it in range(3):
+    torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(); out = _cabi.solve_device(desc, u0_d, par, None, save, None, workspace=None if out is None else out["_workspace"]); e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    acc = out["n_accepted"][:, -1].double(); rej = out["n_rejected"].double()
+    att = (acc.sum() + rej.sum()).item()
+    print(f"iter {it}: {ms:.2f} ms  solves/s={B/ms*1e3:.0f}  attempts={att:.3e}  attempts/s={att/ms*1e3:.3e} acc mean={acc.mean().item():.1f} rej mean={rej.mean().item():.1f} status_bad={(out['status']!=0).sum().item()}")
+print("fp64 peak TF", _cabi.measure_fp64_peak())

@@ -1,0 +1,214 @@
+"""GPU parity tests (run on a B200 with -m gpu): CUDA path through the C ABI vs the CPU oracle.
+
+Thread-per-IVP kernels follow the oracle's operation order with explicit FMAs, so means,
+standard deviations and accepted/rejected counts are compared BIT FOR BIT (rtol = 0), far
+inside the 1e-9 relative tolerance BASELINE.json's north_star states for fp64.
+"""
+
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import problems_util as pu
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cabi():
+    import torch
+
+    assert torch.cuda.is_available(), "these tests need a CUDA device"
+    from odecheckpts_b200 import _cabi
+
+    _cabi.lib()
+    return _cabi
+
+
+def _desc(cabi, problem, d, nu, q, B, K, *, fact="isotropic", corr="ts0", strat="fixedpoint", calib="dynamic",
+          atol=1e-6, rtol=1e-6, dt0=0.01, P=0, flags=0, cap=0, max_attempts=0):  # fmt: skip
+    return cabi.Desc(cabi.PROBLEM_IDS[problem], d, nu, q, cabi.FACTORISATIONS[fact], cabi.CORRECTIONS[corr],
+                     cabi.STRATEGIES[strat], cabi.CALIBRATIONS[calib], atol, rtol, dt0, 0.95, 0.2, 10.0, 0.3, 0.4,
+                     B, K, max_attempts, P, flags, cap)  # fmt: skip
+
+
+def _ocfg(oracle, problem, d, nu, q, **kw):
+    m = dict(fact="factorisation", corr="correction", strat="strategy", calib="calibration", P="num_params")
+    kw2 = {m.get(k, k): v for k, v in kw.items()}
+    return oracle.make_config(problem, d, nu, q, **kw2)
+
+
+def _assert_bitwise(gpu, ora, keys=("u", "u_std", "n_accepted", "n_rejected", "status")):
+    for k in keys:
+        a, b = np.asarray(gpu[k]), np.asarray(ora[k])
+        assert a.shape == b.shape, k
+        same = (a == b) | (np.isnan(a.astype(float)) & np.isnan(b.astype(float)))
+        if not same.all():
+            bad = np.argwhere(~same)[0]
+            raise AssertionError(f"{k}: first mismatch at {tuple(bad)}: gpu={a[tuple(bad)]!r} oracle={b[tuple(bad)]!r}; "
+                                 f"{(~same).sum()} of {same.size} differ")  # fmt: skip
+
+
+CASES = [
+    # problem, d, nu, q, P, params, u0 fn, save_at, kwargs
+    ("logistic", 1, 2, 1, 2, (1.0, 1.0), lambda: np.array([[0.1]]), np.linspace(0, 2.5, 5), dict(atol=1e-3, rtol=1e-3, dt0=0.1)),
+    ("logistic", 1, 4, 1, 2, (1.0, 1.0), lambda: np.array([[0.1]]), np.linspace(0, 2.5, 5), dict(atol=1e-6, rtol=1e-6, dt0=0.1)),
+    ("logistic", 1, 3, 1, 2, (1.0, 1.0), lambda: np.array([[0.1]]), np.linspace(0, 2.5, 7), dict(atol=1e-5, rtol=1e-5, dt0=0.1, fact="dense", corr="ts1")),
+    ("van_der_pol", 1, 4, 2, 1, (1e3,), pu.van_der_pol_u0, np.linspace(0, 6.3, 50), dict(atol=1e-3, rtol=1e-3, fact="dense", corr="ts1")),
+    ("van_der_pol", 1, 4, 2, 1, (1e3,), pu.van_der_pol_u0, np.linspace(0, 6.3, 50), dict(atol=1e-6, rtol=1e-6, fact="dense", corr="ts1")),
+    ("van_der_pol", 1, 3, 2, 1, (1e1,), pu.van_der_pol_u0, np.linspace(0, 6.3, 20), dict(atol=1e-5, rtol=1e-5, fact="dense", corr="ts0")),
+    ("van_der_pol", 1, 5, 2, 1, (1e2,), pu.van_der_pol_u0, np.linspace(0, 6.3, 20), dict(atol=1e-7, rtol=1e-7, fact="isotropic", corr="ts0")),
+    ("van_der_pol", 1, 2, 2, 1, (1e1,), pu.van_der_pol_u0, np.linspace(0, 6.3, 20), dict(atol=1e-4, rtol=1e-4, fact="dense", corr="ts1", calib="none")),
+    ("rigid_body", 3, 2, 1, 3, pu.RIGID_BODY_PARAMS, pu.rigid_body_u0, np.linspace(0, 50, 5), dict(atol=1e-7, rtol=1e-4, dt0=50.0)),
+    ("rigid_body", 3, 4, 1, 3, pu.RIGID_BODY_PARAMS, pu.rigid_body_u0, np.linspace(0, 50, 5), dict(atol=1e-9, rtol=1e-6, dt0=50.0)),
+    ("three_body", 2, 4, 2, 1, (pu.THREE_BODY_MU,), pu.three_body_u0, np.linspace(0, pu.THREE_BODY_T, 50), dict(atol=1e-7, rtol=1e-7, calib="none")),
+    ("three_body", 2, 3, 2, 1, (pu.THREE_BODY_MU,), pu.three_body_u0, np.linspace(0, pu.THREE_BODY_T, 50), dict(atol=1e-5, rtol=1e-5)),
+    ("lotka_volterra", 2, 4, 1, 4, (0.5, 0.05, 0.5, 0.05), lambda: np.array([[20.0, 20.0]]), np.linspace(0, 20, 30), dict(atol=1e-6, rtol=1e-6, dt0=0.1)),
+]
+
+
+@pytest.mark.parametrize("strat", ["fixedpoint", "filter"])
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"{c[0]}-nu{c[2]}-{c[8].get('fact', 'isotropic')}-{c[8].get('corr', 'ts0')}")
+def test_single_ivp_bitwise_vs_oracle(cabi, oracle, case, strat):
+    problem, d, nu, q, P, params, u0fn, save_at, kw = case
+    kw = dict(kw, strat=strat, P=P)
+    u0 = u0fn()
+    K = len(save_at)
+    desc = _desc(cabi, problem, d, nu, q, 1, K, **kw)
+    gpu = cabi.solve_host(desc, u0[None], np.asarray([params]), None, save_at, None, full=True)
+    ora = oracle.solve_save_at(_ocfg(oracle, problem, d, nu, q, **kw), u0, params, save_at, full=True)
+    assert ora["status"] == 0 and int(ora["n_accepted"][-1]) > 10
+    g1 = {k: v[0] for k, v in gpu.items()}
+    _assert_bitwise(g1, ora)
+    np.testing.assert_array_equal(g1["marg_mean"].reshape(K, -1), ora["marg_mean"].reshape(K, -1))
+    np.testing.assert_array_equal(g1["marg_chol"].reshape(K, -1), ora["marg_chol"].reshape(K, -1))
+
+
+def test_vdp_ensemble_bitwise_and_within_tolerance(cabi, oracle):
+    # BASELINE config 2 in miniature: randomised initial conditions, seed 0
+    rng = np.random.default_rng(0)
+    B, K = 96, 50
+    u0 = np.stack([2.0 + 0.5 * rng.uniform(-1, 1, B), 0.5 * rng.uniform(-1, 1, B)], 1).reshape(B, 2, 1)
+    params = np.full((B, 1), 1e3)
+    save_at = np.linspace(0, 6.3, K)
+    kw = dict(atol=1e-6, rtol=1e-6, fact="dense", corr="ts1", P=1)
+    gpu = cabi.solve_host(_desc(cabi, "van_der_pol", 1, 4, 2, B, K, **kw), u0, params, None, save_at, None)
+    ora = oracle.solve_save_at_batch(_ocfg(oracle, "van_der_pol", 1, 4, 2, **kw), u0, params, save_at)
+    assert (ora["status"] == 0).all()
+    # north_star tolerance (1e-9 relative) first, then the stronger bit-for-bit statement
+    np.testing.assert_allclose(gpu["u"], ora["u"], rtol=1e-9, atol=0)
+    np.testing.assert_allclose(gpu["u_std"], ora["u_std"], rtol=1e-9, atol=0)
+    _assert_bitwise(gpu, ora)
+    assert gpu["n_accepted"][:, -1].min() > 10000
+
+
+def test_tolerance_sweep_ensemble_per_member_tol(cabi, oracle):
+    # BASELINE config 3 in miniature: rigid body, 8 tolerances x ICs in ONE launch
+    rng = np.random.default_rng(1)
+    n_ic, tols = 6, 10.0 ** -np.arange(3, 9)
+    u0 = (np.array([1.0, 0.0, 0.9]) + 0.05 * rng.standard_normal((n_ic, 3)))
+    u0 = np.repeat(u0[:, None, :], len(tols), 0).reshape(-1, 1, 3)
+    t = np.tile(tols * 100, n_ic)
+    tol = np.stack([1e-3 * t, t], 1)  # run_simple.py:40-42
+    B, K = len(u0), 5
+    params = np.tile(np.asarray(pu.RIGID_BODY_PARAMS), (B, 1))
+    save_at = np.linspace(0, 50, K)
+    for nu in (2, 4):
+        kw = dict(dt0=50.0, P=3)
+        gpu = cabi.solve_host(_desc(cabi, "rigid_body", 3, nu, 1, B, K, **kw), u0, params, tol, save_at, None)
+        ora = oracle.solve_save_at_batch(_ocfg(oracle, "rigid_body", 3, nu, 1, **kw), u0, params, save_at, tol=tol)
+        _assert_bitwise(gpu, ora)
+
+
+def test_three_body_golden_counts_on_gpu(cabi, goldens):
+    # experiments/5_vs_interpolation/measure.py:44-68,191-192
+    tols = goldens["threebody_tols"]
+    B, K = len(tols), 50
+    u0 = np.tile(pu.three_body_u0()[None], (B, 1, 1))
+    tol = np.stack([tols, tols], 1)
+    desc = _desc(cabi, "three_body", 2, 4, 2, B, K, calib="none", P=1)
+    gpu = cabi.solve_host(desc, u0, np.full((B, 1), pu.THREE_BODY_MU), tol, np.linspace(0, pu.THREE_BODY_T, K), None)
+    np.testing.assert_array_equal(gpu["n_accepted"][:, -1], goldens["threebody_num_steps"])
+
+
+def test_vdp_save_every_step_matches_golden_prefix_and_oracle(cabi, oracle, goldens):
+    # experiments/1_van_der_pol/vdp.py:61-80
+    kw = dict(atol=1e-3, rtol=1e-3, fact="dense", corr="ts1", strat="filter", P=1)
+    cap = 8192
+    desc = _desc(cabi, "van_der_pol", 1, 4, 2, 1, 2, flags=cabi.FLAG_RECORD, cap=cap, **kw)
+    gpu = cabi.solve_host(desc, pu.van_der_pol_u0()[None], np.array([[1e3]]), None, np.array([0.0, 6.3]), None)
+    n = int(gpu["traj_len"][0])
+    t, u = gpu["traj_t"][:n, 0], gpu["traj_u"][:n, 0, 0]
+    ora = oracle.solve_save_every_step(_ocfg(oracle, "van_der_pol", 1, 4, 2, **kw), pu.van_der_pol_u0(), [1e3], 0.0, 6.3)
+    np.testing.assert_array_equal(t, ora["t"])
+    np.testing.assert_array_equal(u, ora["u"][:, 0])
+    np.testing.assert_array_equal(gpu["traj_std"][:n, 0], ora["u_std"][:, 0])
+    grid, sol = goldens["vdp_grid"], goldens["vdp_solution"][:, 0]
+    np.testing.assert_allclose(t[:26], grid[:26], rtol=0, atol=2e-14)
+    np.testing.assert_allclose(u[:26], sol[:26], rtol=0, atol=2e-14)
+    assert abs((n - 1) - (len(grid) - 1)) <= 0.01 * (len(grid) - 1)
+
+
+def test_vdp_fixed_grid_replay_of_the_golden_grid(cabi, oracle, goldens):
+    # vdp.py:88-91: solve_fixed_grid on the adaptive grid
+    grid, sol = goldens["vdp_grid"], goldens["vdp_solution"][:, 0]
+    kw = dict(atol=1e-3, rtol=1e-3, fact="dense", corr="ts1", strat="filter", P=1)
+    desc = _desc(cabi, "van_der_pol", 1, 4, 2, 1, len(grid), flags=cabi.FLAG_FIXED_GRID, **kw)
+    gpu = cabi.solve_host(desc, pu.van_der_pol_u0()[None], np.array([[1e3]]), None, grid, None)
+    ora = oracle.solve_fixed_grid(_ocfg(oracle, "van_der_pol", 1, 4, 2, **kw), pu.van_der_pol_u0(), [1e3], grid)
+    np.testing.assert_array_equal(gpu["u"][0], ora["u"])
+    rel = np.abs(gpu["u"][0, :, 0] - sol) / np.abs(sol)
+    assert np.median(rel) < 1e-9
+
+
+def test_status_words_and_batch_survival(cabi, oracle):
+    # one member hits max_attempts, the rest finish: failure is per member
+    B, K = 4, 10
+    u0 = np.tile(pu.van_der_pol_u0()[None], (B, 1, 1))
+    params = np.array([[1e1], [1e3], [1e1], [1e1]])
+    kw = dict(atol=1e-6, rtol=1e-6, fact="dense", corr="ts1", P=1, max_attempts=3000)
+    save_at = np.linspace(0, 6.3, K)
+    gpu = cabi.solve_host(_desc(cabi, "van_der_pol", 1, 4, 2, B, K, **kw), u0, params, None, save_at, None)
+    ora = oracle.solve_save_at_batch(_ocfg(oracle, "van_der_pol", 1, 4, 2, **kw), u0, params, save_at)
+    assert list(gpu["status"]) == [0, 2, 0, 0] == list(ora["status"])
+    assert np.isnan(gpu["u"][1]).all() and np.isfinite(gpu["u"][[0, 2, 3]]).all()
+    _assert_bitwise(gpu, ora, keys=("u", "u_std", "n_rejected", "status"))
+
+
+def test_many_checkpoints_inside_one_step(cabi, oracle):
+    # several checkpoints fall inside a single accepted step (unpinned by the reference)
+    K = 400
+    save_at = np.linspace(0, 2.5, K)
+    kw = dict(atol=1e-3, rtol=1e-3, dt0=0.1, P=2)
+    for strat in ("fixedpoint", "filter"):
+        gpu = cabi.solve_host(_desc(cabi, "logistic", 1, 4, 1, 1, K, strat=strat, **kw), np.array([[[0.1]]]), np.array([[1.0, 1.0]]), None, save_at, None)
+        ora = oracle.solve_save_at(_ocfg(oracle, "logistic", 1, 4, 1, strat=strat, **kw), np.array([[0.1]]), (1.0, 1.0), save_at)
+        assert int(ora["n_accepted"][-1]) < K / 4
+        _assert_bitwise({k: v[0] for k, v in gpu.items()}, ora)
+        np.testing.assert_allclose(gpu["u"][0, :, 0], pu.logistic_exact(save_at), atol=3e-2)
+
+
+def test_device_pointer_entry_and_public_api(cabi, oracle):
+    import torch
+
+    from odecheckpts_b200 import ivps, ivpsolvers
+
+    vf, u0, tspan, args = ivps.logistic()
+    save_at = np.linspace(*tspan, num=5)
+    solve = ivpsolvers.solve("ts0-4", vf, u0[0], save_at=save_at, dt0=0.1, atol=1e-3, rtol=1e-3)
+    # host path (numpy)
+    sol_h, aux = solve(u0, args)
+    assert "u0_solve" in aux and sol_h.shape == (5, 1)
+    np.testing.assert_allclose(sol_h[:, 0], pu.logistic_exact(save_at), atol=np.sqrt(1e-3), rtol=np.sqrt(1e-3))
+    # device path (torch CUDA tensors in -> torch CUDA tensors out), batched
+    B = 33
+    u0_b = torch.linspace(0.05, 0.5, B, dtype=torch.float64, device="cuda")[:, None]
+    sol_d, _ = solve((u0_b,), args)
+    assert sol_d.is_cuda and tuple(sol_d.shape) == (B, 5, 1)
+    ora = oracle.solve_save_at_batch(
+        oracle.make_config("logistic", 1, 4, 1, atol=1e-3, rtol=1e-3, dt0=0.1, num_params=2),
+        u0_b.cpu().numpy().reshape(B, 1, 1), np.tile([1.0, 1.0], (B, 1)), save_at)  # fmt: skip
+    np.testing.assert_array_equal(sol_d.cpu().numpy(), ora["u"])
+    with pytest.raises(ValueError, match="Tuple expected."):
+        solve(u0[0], args)
