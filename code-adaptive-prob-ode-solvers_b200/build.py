@@ -50,7 +50,8 @@ def build(force=False, verbose=False):
 
     def compile_one(job):
         s, o = job
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+        extra = os.environ.get("PN_EXTRA_NVCC_FLAGS", "").split()
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
         r = subprocess.run(cmd, capture_output=True, text=True)
         return s, r.returncode, r.stdout + r.stderr
 

@@ -54,6 +54,19 @@ static void prior_lq(int nu, double* lq /* n*n row-major */) {
   for (int i = 0; i < n * n; ++i) lq[i] = (double)Lc[i];
 }
 
+// optional kernel timing (pn_b200_set_profiling)
+static bool g_profiling = false;
+static cudaEvent_t g_ev[4];
+static bool g_ev_ready = false, g_ev_recorded = false;
+
+struct Geometry {
+  int dev;
+  const KernelEntry* k;
+  int num_sms, ctas_per_sm;
+};
+static std::vector<Geometry> g_geom;
+static std::mutex g_geom_mutex;
+
 struct Plan {
   const KernelEntry* k = nullptr;
   int grid = 0, ctas_per_sm = 0, num_sms = 0;
@@ -102,17 +115,29 @@ static int make_plan(const pn_b200_desc* d, Plan* p, bool need_device) {
   int dev = 0;
   cudaError_t ce = cudaGetDevice(&dev);
   if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, cudaGetErrorString(ce));
-  cudaDeviceProp prop;
-  ce = cudaGetDeviceProperties(&prop, dev);
-  if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, cudaGetErrorString(ce));
-  p->num_sms = prop.multiProcessorCount;
-  ce = cudaFuncSetAttribute(p->k->solve_func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
-  if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce));
-  int occ = 0;
-  ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, p->k->solve_func, p->k->threads, p->smem);
-  if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, cudaGetErrorString(ce));
-  if (occ < 1) return fail(PN_B200_ERR_CUDA, "kernel does not fit on an SM");
-  p->ctas_per_sm = occ;
+  // launch geometry is cached per (device, kernel): the attribute / occupancy queries are not free
+  {
+    std::lock_guard<std::mutex> lock(g_geom_mutex);
+    for (const auto& g : g_geom)
+      if (g.dev == dev && g.k == p->k) {
+        p->num_sms = g.num_sms;
+        p->ctas_per_sm = g.ctas_per_sm;
+      }
+  }
+  if (p->ctas_per_sm == 0) {
+    ce = cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, cudaGetErrorString(ce));
+    ce = cudaFuncSetAttribute(p->k->solve_func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
+    if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce));
+    int occ = 0;
+    ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, p->k->solve_func, p->k->threads, p->smem);
+    if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, cudaGetErrorString(ce));
+    if (occ < 1) return fail(PN_B200_ERR_CUDA, "kernel does not fit on an SM");
+    p->ctas_per_sm = occ;
+    std::lock_guard<std::mutex> lock(g_geom_mutex);
+    g_geom.push_back({dev, p->k, p->num_sms, occ});
+  }
+  const int occ = p->ctas_per_sm;
   long long want = (d->batch + p->k->threads - 1) / p->k->threads;
   long long cap = (long long)occ * p->num_sms;
   p->grid = (int)(want < cap ? want : cap);
@@ -138,6 +163,14 @@ __global__ void __launch_bounds__(256) pn_dfma_peak_kernel(double* out, double a
 #pragma unroll
   for (int i = 0; i < 16; ++i) s += x[i];
   if (s == 123456.789) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+__global__ void pn_selftest_math_kernel(const double* x, const double* y, double* r, double* sq, double* pw, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  r[i] = rcp(x[i]);
+  sq[i] = dsqrt(fabs(x[i]));
+  pw[i] = det_pow(fabs(x[i]), y[i]);
 }
 
 }  // namespace pn
@@ -232,8 +265,18 @@ int pn_b200_solve_save_at(const pn_b200_desc* desc, const double* u0, const doub
 
   cudaError_t ce = cudaMemsetAsync(workspace, 0, p.ws_ticket, stream);
   if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, cudaGetErrorString(ce));
+  const bool prof = g_profiling;
+  if (prof && !g_ev_ready) {
+    for (auto& e : g_ev) cudaEventCreate(&e);
+    g_ev_ready = true;
+  }
+  if (prof) cudaEventRecord(g_ev[0], stream);
   ce = p.k->launch_solve(a, p.grid, p.smem, stream);
   if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, std::string("solve kernel launch: ") + cudaGetErrorString(ce));
+  if (prof) {
+    cudaEventRecord(g_ev[1], stream);
+    cudaEventRecord(g_ev[2], stream);
+  }
 
   SmoothArgs s;
   s.B = desc->batch;
@@ -246,6 +289,24 @@ int pn_b200_solve_save_at(const pn_b200_desc* desc, const double* u0, const doub
   s.marg_chol = marg_chol;
   ce = p.k->launch_smooth(s, stream);
   if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, std::string("smoothing kernel launch: ") + cudaGetErrorString(ce));
+  if (prof) {
+    cudaEventRecord(g_ev[3], stream);
+    g_ev_recorded = true;
+  }
+  return PN_B200_SUCCESS;
+}
+
+int pn_b200_set_profiling(int enable) {
+  g_profiling = enable != 0;
+  return PN_B200_SUCCESS;
+}
+
+int pn_b200_get_last_timing(float* solve_ms, float* smooth_ms) {
+  if (!g_ev_recorded) return fail(PN_B200_ERR_ARGUMENT, "no profiled solve has been issued");
+  cudaError_t ce = cudaEventSynchronize(g_ev[3]);
+  if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, cudaGetErrorString(ce));
+  cudaEventElapsedTime(solve_ms, g_ev[0], g_ev[1]);
+  cudaEventElapsedTime(smooth_ms, g_ev[2], g_ev[3]);
   return PN_B200_SUCCESS;
 }
 
@@ -325,6 +386,12 @@ int pn_b200_solve_save_at_host(const pn_b200_desc* desc, const double* u0, const
   cudaStreamSynchronize(stream);
   cudaStreamDestroy(stream);
   return rc;
+}
+
+// Test hook (not part of the public header): evaluates the kernels' branch-free rcp / sqrt / pow.
+int pn_b200_selftest_math(const double* x, const double* y, double* r, double* sq, double* pw, long long n) {
+  pn_selftest_math_kernel<<<(unsigned)((n + 255) / 256), 256>>>(x, y, r, sq, pw, n);
+  return cudaGetLastError() == cudaSuccess ? 0 : PN_B200_ERR_CUDA;
 }
 
 int pn_b200_measure_fp64_peak(double* tflops, void* cuda_stream) {

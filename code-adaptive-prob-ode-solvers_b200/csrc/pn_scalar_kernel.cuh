@@ -103,7 +103,10 @@ struct Layout {
 };
 
 template <class Prob, int NU, int STRAT, int THREADS>
-__global__ void __launch_bounds__(THREADS) pn_scalar_kernel(const __grid_constant__ SolveArgs a) {
+#ifndef PN_MINBLOCKS
+#define PN_MINBLOCKS 2
+#endif
+__global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const __grid_constant__ SolveArgs a) {
   constexpr int N = NU + 1, D = Prob::D, Q = Prob::Q, P = (Prob::P > 0 ? Prob::P : 1);
   using Lay = Layout<N, D>;
   constexpr bool FIX = (STRAT == 1);
@@ -120,7 +123,7 @@ __global__ void __launch_bounds__(THREADS) pn_scalar_kernel(const __grid_constan
   constexpr int OFF_G = 0, OFF_g = N * N, OFF_LAM = N * N + N * D;
 
   const double* LQ = a.lq;
-  const double sqrt_d = dsqrt((double)D);
+  const double inv_sqrt_d = rcp(dsqrt((double)D));
 
   // ---- per-lane persistent state --------------------------------------------------------
   bool have = false, exhausted = false;
@@ -132,6 +135,10 @@ __global__ void __launch_bounds__(THREADS) pn_scalar_kernel(const __grid_constan
   double L[N][N];  // lower triangle used
   int mode = MODE_STEP;
   long long k_next = 1, n_acc = 0, n_rej = 0, n_att = 0;
+  // utilisation statistics (per warp, flushed once at exit): loop iterations, lane-iterations with
+  // work, lane-iterations spent on checkpoint interpolation
+  unsigned long long stat_warp_iters = 0, stat_lane_iters = 0, stat_interp_iters = 0;
+  const long long clk0 = clock64();
 
   for (;;) {
     // ---- fetch a member ----------------------------------------------------------------
@@ -187,8 +194,20 @@ __global__ void __launch_bounds__(THREADS) pn_scalar_kernel(const __grid_constan
         exhausted = true;
       }
     }
-    if (!__any_sync(0xffffffffu, have)) break;
-    if (!have) continue;  // idle lane; the warp-level vote above keeps the loop convergent
+    // warp-level vote keeps the loop convergent; the lane counts feed the utilisation statistics
+#ifdef PN_CTA_LOCKSTEP
+    // CTA-wide lockstep: the 4 warps of a CTA sit on the 4 SM sub-partitions and fetch the same
+    // instructions at the same time (one instruction stream per CTA instead of one per warp)
+    if (!__syncthreads_or(have)) break;
+    const unsigned active = __ballot_sync(0xffffffffu, have);
+#else
+    const unsigned active = __ballot_sync(0xffffffffu, have);
+    if (active == 0u) break;
+#endif
+    stat_warp_iters += 1;
+    stat_lane_iters += __popc(active);
+    stat_interp_iters += __popc(__ballot_sync(0xffffffffu, have && mode != MODE_STEP));
+    if (!have) continue;  // idle lane
 
     // ---- choose this iteration's prediction --------------------------------------------
     double t_ck = a.save_at[k_next < a.K ? k_next : a.K - 1];
@@ -273,7 +292,7 @@ __global__ void __launch_bounds__(THREADS) pn_scalar_kernel(const __grid_constan
       double zz = 0.0;
 #pragma unroll
       for (int c = 0; c < D; ++c) zz = fma(z[c], z[c], zz);
-      double sigma_hat = (dsqrt(zz) / s) / sqrt_d;
+      double sigma_hat = (dsqrt(zz) * rcp(s)) * inv_sqrt_d;
       err = (fabs(dt) * sigma_hat) * s;
       sigma = (mode == MODE_STEP) ? ((a.calibration == 1) ? sigma_hat : sigma_given) : sigma_given;
     }
@@ -527,16 +546,17 @@ __global__ void __launch_bounds__(THREADS) pn_scalar_kernel(const __grid_constan
       double acc = 0.0;
 #pragma unroll
       for (int c = 0; c < D; ++c) {
-        double ratio = err / fma(rtol, fabs(m_new[0][c]), atol);
+        double ratio = err * rcp(fma(rtol, fabs(m_new[0][c]), atol));
         acc = fma(ratio, ratio, acc);
       }
-      e_norm = dsqrt(acc) / sqrt_d;
+      e_norm = dsqrt(acc) * inv_sqrt_d;
     }
     // PI controller
     double fac;
     {
-      double a1 = det_pow(1.0 / e_norm, a.pow_i);
-      double a2 = det_pow(e_prev / e_norm, a.pow_p);
+      double ie = rcp(e_norm);
+      double a1 = det_pow(ie, a.pow_i);
+      double a2 = det_pow(e_prev * ie, a.pow_p);
       fac = (a.safety * a1) * a2;
       fac = (fac < a.factor_max) ? fac : a.factor_max;
       fac = (fac > a.factor_min) ? fac : a.factor_min;
@@ -736,6 +756,12 @@ __global__ void __launch_bounds__(THREADS) pn_scalar_kernel(const __grid_constan
       if (a.flags & FLAG_RECORD) a.traj_len[b] = (n_acc + 1 < a.traj_cap) ? (n_acc + 1) : a.traj_cap;
       have = false;
     }
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(a.ticket + 1, stat_warp_iters);
+    atomicAdd(a.ticket + 2, stat_lane_iters);
+    atomicAdd(a.ticket + 3, stat_interp_iters);
+    atomicMax((long long*)a.ticket + 4, (long long)(clock64() - clk0));
   }
 #undef SBW
 #undef SPEND

@@ -81,6 +81,8 @@ EXPORTS = (
     "pn_b200_solve_save_at_host",
     "pn_b200_get_kernel_info",
     "pn_b200_measure_fp64_peak",
+    "pn_b200_set_profiling",
+    "pn_b200_get_last_timing",
     "pn_b200_last_error",
 )
 
@@ -114,6 +116,10 @@ def lib():
         L.pn_b200_get_kernel_info.argtypes = [C.POINTER(Desc), C.POINTER(KernelInfo)]
         L.pn_b200_measure_fp64_peak.restype = C.c_int
         L.pn_b200_measure_fp64_peak.argtypes = [C.POINTER(C.c_double), vp]
+        L.pn_b200_set_profiling.restype = C.c_int
+        L.pn_b200_set_profiling.argtypes = [C.c_int]
+        L.pn_b200_get_last_timing.restype = C.c_int
+        L.pn_b200_get_last_timing.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.pn_b200_last_error.restype = C.c_char_p
         L.pn_b200_last_error.argtypes = []
         _lib = L
@@ -153,6 +159,17 @@ def measure_fp64_peak(stream=0):
     out = C.c_double(0.0)
     check(lib().pn_b200_measure_fp64_peak(C.byref(out), C.c_void_p(stream)))
     return out.value
+
+
+def set_profiling(enable):
+    check(lib().pn_b200_set_profiling(C.c_int(1 if enable else 0)))
+
+
+def last_timing():
+    """(solver-kernel ms, smoothing-kernel ms) of the last profiled solve; waits for it."""
+    a, b = C.c_float(0), C.c_float(0)
+    check(lib().pn_b200_get_last_timing(C.byref(a), C.byref(b)))
+    return a.value, b.value
 
 
 def _np_ptr(a):

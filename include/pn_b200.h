@@ -117,6 +117,12 @@ int pn_b200_get_kernel_info(const pn_b200_desc* desc, pn_b200_kernel_info* info)
  * TFLOP/s (the roofline denominator; MEASURED_PEAKS.json carries no fp64 entry). */
 int pn_b200_measure_fp64_peak(double* tflops, void* cuda_stream);
 
+/* Optional per-kernel timing for reports: when enabled, pn_b200_solve_save_at brackets its two
+ * kernels (the persistent solver loop and the smoothing sweep) with CUDA events on the caller's
+ * stream; pn_b200_get_last_timing waits for them and returns their durations in milliseconds. */
+int pn_b200_set_profiling(int enable);
+int pn_b200_get_last_timing(float* solve_ms, float* smooth_ms);
+
 /* Human-readable description of the last error on the calling thread. */
 const char* pn_b200_last_error(void);
 

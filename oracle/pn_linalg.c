@@ -101,7 +101,7 @@ double pn_det_log(double x) {
     m = m * 2.0;
     k -= 1;
   }
-  double s = (m - 1.0) / (m + 1.0);
+  double s = (m - 1.0) * (1.0 / (m + 1.0));
   double z = s * s;
   /* log(m) = 2 s (1 + z/3 + z^2/5 + ... + z^11/23), |s| <= 0.1716 */
   double P = 1.0 / 23.0;

@@ -77,7 +77,7 @@ typedef struct {
   int dense;         /* r > 1 path */
   double *A, *LQ;    /* N x N (Kronecker-expanded for dense d>1) */
   double fact[PN_MAX_N], invfact[PN_MAX_N];
-  double sqrt_d, sqrt_C;
+  double inv_sqrt_d, inv_sqrt_C;
   /* workspaces */
   double *p, *pinv;              /* N */
   double *m_p, *m_ext_p, *m_ext; /* N*Ctot */
@@ -146,8 +146,8 @@ static int engine_init(engine *E, const pn_oracle_config *cfg) {
     E->fact[k] = f;
     E->invfact[k] = 1.0 / f;
   }
-  E->sqrt_d = sqrt((double)d);
-  E->sqrt_C = sqrt((double)E->C);
+  E->inv_sqrt_d = 1.0 / sqrt((double)d);
+  E->inv_sqrt_C = 1.0 / sqrt((double)E->C);
   size_t NN = (size_t)N * N, NC = (size_t)N * E->Ctot;
   E->p = dalloc(N); E->pinv = dalloc(N);
   E->m_p = dalloc(NC); E->m_ext_p = dalloc(NC); E->m_ext = dalloc(NC);
@@ -409,7 +409,7 @@ static void calibrate_and_estimate(engine *E, double dt) {
       int c0 = f * E->C;
       double zz = 0.0;
       for (int c = c0; c < c0 + E->C; ++c) zz = fma(E->z[c], E->z[c], zz);
-      double sigma_hat = (sqrt(zz) / s) / E->sqrt_C;
+      double sigma_hat = (sqrt(zz) * (1.0 / s)) * E->inv_sqrt_C;
       E->sig[f] = sigma_hat;
       double er = (adt * sigma_hat) * s;
       for (int c = c0; c < c0 + E->C; ++c) E->err[c] = er;
@@ -429,7 +429,7 @@ static void calibrate_and_estimate(engine *E, double dt) {
     pn_solve_upper_transposed(Rs, E->z, y, d, 1);
     double yy = 0.0;
     for (int l = 0; l < d; ++l) yy = fma(y[l], y[l], yy);
-    double sigma_hat = sqrt(yy) / E->sqrt_d;
+    double sigma_hat = sqrt(yy) * E->inv_sqrt_d;
     E->sig[0] = sigma_hat;
     for (int l = 0; l < d; ++l) {
       double cc = 0.0;
@@ -513,8 +513,9 @@ typedef struct {
 static double pi_factor(const engine *E, double e, double e_prev) {
   double nn = (double)(E->nu + 1);
   double n1 = E->cfg.power_integral / nn, n2 = E->cfg.power_proportional / nn;
-  double a1 = pn_det_pow(1.0 / e, n1);
-  double a2 = pn_det_pow(e_prev / e, n2);
+  double ie = 1.0 / e;
+  double a1 = pn_det_pow(ie, n1);
+  double a2 = pn_det_pow(e_prev * ie, n2);
   double fac = (E->cfg.safety * a1) * a2;
   fac = (fac < E->cfg.factor_max) ? fac : E->cfg.factor_max;
   fac = (fac > E->cfg.factor_min) ? fac : E->cfg.factor_min;
@@ -554,10 +555,10 @@ static void attempt_step(engine *E, const double *params, const pstate *S, doubl
   /* scaled error norm: uses the PROPOSED u only (App. A.3, quirk confirmed against the golden) */
   double acc = 0.0;
   for (int l = 0; l < d; ++l) {
-    double ratio = E->err[l] / fma(rtol, fabs(P->mean[l]), atol);
+    double ratio = E->err[l] * (1.0 / fma(rtol, fabs(P->mean[l]), atol));
     acc = fma(ratio, ratio, acc);
   }
-  double e = sqrt(acc) / E->sqrt_d;
+  double e = sqrt(acc) * E->inv_sqrt_d;
   info->error_norm = e;
   info->dt_proposed = pi_factor(E, e, e_prev) * dt;
   info->sigma = P->sigma[0];
