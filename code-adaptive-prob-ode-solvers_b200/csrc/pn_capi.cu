@@ -93,6 +93,13 @@ static int resolve(const pn_b200_desc* d, const KernelEntry** out) {
                    (d->factorisation == PN_B200_DENSE && d->d == 1) ||
                    (d->factorisation == PN_B200_BLOCKDIAG && d->d == 1 && d->correction == PN_B200_TS0);
   if (scalar_ok) k = find_kernel(FAMILY_SCALAR, d->problem, d->nu, d->strategy);
+  // lane-per-dimension family: blockdiag EKF0, and isotropic EKF0 for problems too wide for one thread
+  if (!k && d->correction == PN_B200_TS0 && d->factorisation == PN_B200_BLOCKDIAG)
+    k = find_kernel(FAMILY_GROUP_BDIAG, d->problem, d->nu, d->strategy);
+  if (!k && d->correction == PN_B200_TS0 && d->factorisation == PN_B200_ISOTROPIC)
+    k = find_kernel(FAMILY_GROUP_ISO, d->problem, d->nu, d->strategy);
+  if (k && k->group > 1 && (d->flags & PN_B200_FLAG_RECORD))
+    return fail(PN_B200_ERR_UNSUPPORTED, "trajectory recording is implemented for the thread-per-IVP kernels");
   if (!k) {
     char buf[256];
     snprintf(buf, sizeof buf, "no kernel compiled for problem=%d nu=%d factorisation=%d correction=%d strategy=%d d=%d",
@@ -110,7 +117,7 @@ static int make_plan(const pn_b200_desc* d, Plan* p, bool need_device) {
   int rc = resolve(d, &p->k);
   if (rc) return rc;
   p->smem = (size_t)p->k->smem_doubles * p->k->threads * sizeof(double);
-  p->ws_cond = (size_t)d->num_save_at * p->k->slot_doubles * (size_t)d->batch * sizeof(double);
+  p->ws_cond = (size_t)d->num_save_at * p->k->slot_doubles * (size_t)d->batch * p->k->dv * sizeof(double);
   if (!need_device) return PN_B200_SUCCESS;
   int dev = 0;
   cudaError_t ce = cudaGetDevice(&dev);
@@ -138,7 +145,8 @@ static int make_plan(const pn_b200_desc* d, Plan* p, bool need_device) {
     g_geom.push_back({dev, p->k, p->num_sms, occ});
   }
   const int occ = p->ctas_per_sm;
-  long long want = (d->batch + p->k->threads - 1) / p->k->threads;
+  const long long per_cta = p->k->threads / p->k->group;  // IVPs a CTA holds at a time
+  long long want = (d->batch + per_cta - 1) / per_cta;
   long long cap = (long long)occ * p->num_sms;
   p->grid = (int)(want < cap ? want : cap);
   if (p->grid < 1) p->grid = 1;
@@ -281,6 +289,8 @@ int pn_b200_solve_save_at(const pn_b200_desc* desc, const double* u0, const doub
   SmoothArgs s;
   s.B = desc->batch;
   s.K = desc->num_save_at;
+  s.dv = p.k->dv;
+  s.chol_per_dim = (p.k->family == FAMILY_GROUP_BDIAG) ? 1 : 0;
   s.cond = a.cond;
   s.status = status;
   s.u = u;
@@ -343,7 +353,7 @@ int pn_b200_solve_save_at_host(const pn_b200_desc* desc, const double* u0, const
       {&d_u, nullptr, u, B * K * d * 8},
       {&d_std, nullptr, u_std, B * K * d * 8},
       {&d_mm, nullptr, marg_mean, marg_mean ? B * K * n * d * 8 : 0},
-      {&d_mc, nullptr, marg_chol, marg_chol ? B * K * n * n * 8 : 0},
+      {&d_mc, nullptr, marg_chol, marg_chol ? B * K * (k->family == FAMILY_GROUP_BDIAG ? d : 1) * n * n * 8 : 0},
       {&d_nacc, nullptr, n_accepted, B * K * 8},
       {&d_nrej, nullptr, n_rejected, B * 8},
       {&d_stat, nullptr, status, B * 4},

@@ -195,6 +195,60 @@ struct ThreeBody {
   }
 };
 
+// ---- Pleiades, second order: 7 bodies, masses 1..7 (ivps.py:59-99) ------------------------
+// u = (x[7], y[7]);  a_i = sum_{j != i} m_j (r_j - r_i) / |r_j - r_i|^3
+struct Pleiades {
+  static constexpr int D = 14, Q = 2, P = 0, ID = 3;
+  static constexpr bool HAS_JAC = false;
+  PN_DEV static void vf(const double* u, const double*, double* f) {
+    const double *x = u, *y = u + 7;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+      double ax = 0.0, ay = 0.0;
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        if (j == i) continue;
+        double dx = x[j] - x[i], dy = y[j] - y[i];
+        double p = inv_pow32(fma(dy, dy, dx * dx));
+        ax = fma((double)(j + 1), p * dx, ax);
+        ay = fma((double)(j + 1), p * dy, ay);
+      }
+      f[i] = ax;
+      f[7 + i] = ay;
+    }
+  }
+  PN_DEV static void jac(const double*, const double*, double*) {}
+  template <int N>
+  PN_DEV static void vf_jet(const double* U, const double*, double* F) {
+    const double *x = U, *y = U + 7 * N;
+    for (int i = 0; i < 7; ++i) {
+      double* ax = F + i * N;
+      double* ay = F + (7 + i) * N;
+      for (int k = 0; k < N; ++k) ax[k] = ay[k] = 0.0;
+      for (int j = 0; j < 7; ++j) {
+        if (j == i) continue;
+        double dx[N], dy[N], s[N], p[N], t1[N], t2[N];
+        const double mj = (double)(j + 1);
+        for (int k = 0; k < N; ++k) {
+          dx[k] = x[j * N + k] - x[i * N + k];
+          dy[k] = y[j * N + k] - y[i * N + k];
+        }
+        jet_mul<N>(dx, dx, t1);
+        jet_mul<N>(dy, dy, t2);
+        s[0] = fma(dy[0], dy[0], dx[0] * dx[0]);
+        for (int k = 1; k < N; ++k) s[k] = t2[k] + t1[k];
+        jet_inv_pow32<N>(s, p);
+        jet_mul<N>(p, dx, t1);
+        jet_mul<N>(p, dy, t2);
+        for (int k = 0; k < N; ++k) {
+          ax[k] = fma(mj, t1[k], ax[k]);
+          ay[k] = fma(mj, t2[k], ay[k]);
+        }
+      }
+    }
+  }
+};
+
 // taylor.odejet_padded_scan replacement: tc[k][l] = u_l^{(k)}(t0), k = 0..NU.
 template <class Prob, int NU>
 PN_DEV void taylor_init(const double* u0 /*[Q*D]*/, const double* par, double (&tc)[NU + 1][Prob::D]) {

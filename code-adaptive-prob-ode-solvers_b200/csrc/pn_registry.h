@@ -7,7 +7,11 @@
 
 namespace pn {
 
-enum : int { FAMILY_SCALAR = 0 /* thread per IVP, n x n factors */ };
+enum : int {
+  FAMILY_SCALAR = 0,      // thread per IVP, one n x n factor shared by all mean columns
+  FAMILY_GROUP_ISO = 1,   // lane per dimension, identical factors (isotropic)
+  FAMILY_GROUP_BDIAG = 2  // lane per dimension, per-dimension factors (blockdiag)
+};
 
 struct KernelEntry {
   int family, problem, nu, strategy;
@@ -15,6 +19,8 @@ struct KernelEntry {
   int slot_doubles;   // workspace doubles per (checkpoint, member)
   int smem_doubles;   // dynamic shared memory doubles per thread
   int threads;
+  int group;          // lanes per IVP (1: thread per IVP)
+  int dv;             // lanes per IVP that own state (workspace entries per member)
   bool has_jac;
   const void* solve_func;
   cudaError_t (*launch_solve)(const SolveArgs&, int grid, size_t smem, cudaStream_t);
@@ -24,21 +30,25 @@ struct KernelEntry {
 void register_kernel(const KernelEntry& e);
 const KernelEntry* find_kernel(int family, int problem, int nu, int strategy);
 
-template <class Prob, int NU, int STRAT, int THREADS>
+template <class Prob, int NU, int STRAT, int GROUP, int BDIAG, int THREADS>
 struct ScalarInstance {
+  static constexpr int DL = (GROUP > 1) ? 1 : Prob::D;  // mean columns per lane
+  static constexpr int DV = (GROUP > 1) ? Prob::D : 1;
   static cudaError_t launch_solve(const SolveArgs& a, int grid, size_t smem, cudaStream_t s) {
-    pn_scalar_kernel<Prob, NU, STRAT, THREADS><<<grid, THREADS, smem, s>>>(a);
+    pn_scalar_kernel<Prob, NU, STRAT, GROUP, BDIAG, THREADS><<<grid, THREADS, smem, s>>>(a);
     return cudaGetLastError();
   }
   static cudaError_t launch_smooth(const SmoothArgs& a, cudaStream_t s) {
-    int grid = (int)((a.B + 127) / 128);
-    pn_smooth_kernel<NU + 1, Prob::D, STRAT><<<grid, 128, 0, s>>>(a);
+    int grid = (int)((a.B * a.dv + 127) / 128);
+    pn_smooth_kernel<NU + 1, DL, STRAT><<<grid, 128, 0, s>>>(a);
     return cudaGetLastError();
   }
   static KernelEntry entry() {
-    using Lay = Layout<NU + 1, Prob::D>;
+    using Lay = Layout<NU + 1, DL>;
     KernelEntry e;
-    e.family = FAMILY_SCALAR;
+    e.family = (GROUP == 1) ? FAMILY_SCALAR : (BDIAG ? FAMILY_GROUP_BDIAG : FAMILY_GROUP_ISO);
+    e.group = GROUP;
+    e.dv = DV;
     e.problem = Prob::ID;
     e.nu = NU;
     e.strategy = STRAT;
@@ -50,7 +60,7 @@ struct ScalarInstance {
     e.smem_doubles = ((STRAT == 1) ? Lay::BW : 0) + Lay::PEND;
     e.threads = THREADS;
     e.has_jac = Prob::HAS_JAC;
-    e.solve_func = (const void*)&pn_scalar_kernel<Prob, NU, STRAT, THREADS>;
+    e.solve_func = (const void*)&pn_scalar_kernel<Prob, NU, STRAT, GROUP, BDIAG, THREADS>;
     e.launch_solve = &launch_solve;
     e.launch_smooth = &launch_smooth;
     return e;
@@ -64,6 +74,9 @@ struct Registrar {
 #define PN_CAT2(a, b) a##b
 #define PN_CAT(a, b) PN_CAT2(a, b)
 #define PN_REGISTER_SCALAR(Prob, NU, STRAT) \
-  static ::pn::Registrar PN_CAT(pn_reg_, __COUNTER__)(::pn::ScalarInstance<::pn::Prob, NU, STRAT, 128>::entry())
+  static ::pn::Registrar PN_CAT(pn_reg_, __COUNTER__)(::pn::ScalarInstance<::pn::Prob, NU, STRAT, 1, 0, 128>::entry())
+// lane-per-dimension kernels: GROUP lanes per IVP, BDIAG = 1 blockdiag / 0 isotropic
+#define PN_REGISTER_GROUP(Prob, NU, STRAT, GROUP, BDIAG) \
+  static ::pn::Registrar PN_CAT(pn_reg_, __COUNTER__)(::pn::ScalarInstance<::pn::Prob, NU, STRAT, GROUP, BDIAG, 128>::entry())
 
 }  // namespace pn

@@ -102,12 +102,69 @@ struct Layout {
   __host__ __device__ static constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }  // j <= i
 };
 
-template <class Prob, int NU, int STRAT, int THREADS>
+// butterfly sum over the GROUP lanes of one IVP (all lanes end with the same bits)
+template <int GROUP>
+PN_DEV double group_sum(double v, unsigned gmask) {
+#pragma unroll
+  for (int off = GROUP / 2; off >= 1; off >>= 1) v = v + __shfl_xor_sync(gmask, v, off);
+  return v;
+}
+
+// Vector field for the lane-per-dimension kernels: every lane holds ITS dimension's predicted
+// (u, u', ...) and gets back ITS component of f.  Default: gather everything with shuffles,
+// evaluate the whole field, select the own component.
+template <class Prob, int GROUP>
+struct GroupVf {
+  PN_DEV static double eval(const double* own /*[Q]*/, int sub, int base, unsigned gmask, const double* par) {
+    constexpr int DT = Prob::D, Q = Prob::Q;
+    double u[Q * DT], f[DT];
+#pragma unroll
+    for (int k = 0; k < Q; ++k)
+#pragma unroll
+      for (int c = 0; c < DT; ++c) u[k * DT + c] = __shfl_sync(gmask, own[k], base + c);
+    Prob::vf(u, par, f);
+    double r = f[0];
+#pragma unroll
+    for (int c = 1; c < DT; ++c) r = (sub == c) ? f[c] : r;
+    return r;
+  }
+};
+
+// Pleiades: lane c < 7 owns x_c, lane 7 + i owns y_i; each lane sums its 6 pair terms.
+template <int GROUP>
+struct GroupVf<Pleiades, GROUP> {
+  PN_DEV static double eval(const double* own, int sub, int base, unsigned gmask, const double*) {
+    const int i = (sub < 7) ? sub : ((sub < 14) ? sub - 7 : 0);
+    const bool isx = sub < 7;
+    const double xi = __shfl_sync(gmask, own[0], base + i);
+    const double yi = __shfl_sync(gmask, own[0], base + 7 + i);
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      const double xj = __shfl_sync(gmask, own[0], base + j);
+      const double yj = __shfl_sync(gmask, own[0], base + 7 + j);
+      const double dx = xj - xi, dy = yj - yi;
+      const double pw = inv_pow32(fma(dy, dy, dx * dx));
+      const double term = fma((double)(j + 1), pw * (isx ? dx : dy), acc);
+      acc = (j == i) ? acc : term;  // nan_to_num(0/0) = 0 (ivps.py:95-96)
+    }
+    return acc;
+  }
+};
+
 #ifndef PN_MINBLOCKS
 #define PN_MINBLOCKS 2
 #endif
+// GROUP = 1: one thread per IVP, the factor is shared by the Prob::D mean columns the thread holds.
+// GROUP > 1: GROUP lanes per IVP, lane `sub` owns ODE dimension `sub` (one mean column) and a full
+//            n x n factor set: per-dimension factors for BDIAG (blockdiag factorisation), replicated
+//            identical factors for the isotropic factorisation.
+template <class Prob, int NU, int STRAT, int GROUP, int BDIAG, int THREADS>
 __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const __grid_constant__ SolveArgs a) {
-  constexpr int N = NU + 1, D = Prob::D, Q = Prob::Q, P = (Prob::P > 0 ? Prob::P : 1);
+  constexpr int N = NU + 1, DT = Prob::D, D = (GROUP > 1) ? 1 : DT, Q = Prob::Q, P = (Prob::P > 0 ? Prob::P : 1);
+  constexpr int DV = (GROUP > 1) ? DT : 1;  // lanes ("virtual members") per IVP that own state
+  static_assert(GROUP == 1 || (GROUP >= DT && (GROUP & (GROUP - 1)) == 0 && GROUP <= 32), "bad GROUP");
+  static_assert(GROUP > 1 || BDIAG == 0, "blockdiag with one thread per IVP only makes sense for d == 1");
   using Lay = Layout<N, D>;
   constexpr bool FIX = (STRAT == 1);
   constexpr int SLOT = FIX ? Lay::SLOT_FIX : Lay::SLOT_FILT;
@@ -123,11 +180,17 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
   constexpr int OFF_G = 0, OFF_g = N * N, OFF_LAM = N * N + N * D;
 
   const double* LQ = a.lq;
-  const double inv_sqrt_d = rcp(dsqrt((double)D));
+  const double inv_sqrt_d = rcp(dsqrt((double)DT));
+  const int lane = threadIdx.x & 31;
+  const int sub = (GROUP > 1) ? (lane & (GROUP - 1)) : 0;   // dimension owned by this lane
+  const int base = lane - sub;                               // first lane of the group
+  const unsigned gmask = (GROUP >= 32) ? 0xffffffffu : (((1u << GROUP) - 1u) << base);
+  const bool real = sub < DT;                                // padding lanes carry no dimension
+  const long long VB = a.B * DV;                             // stride of the member-minor workspace
 
   // ---- per-lane persistent state --------------------------------------------------------
   bool have = false, exhausted = false;
-  long long b = 0;
+  long long b = 0, vb = 0;
   double t = 0.0, dt_next = 0.0, e_prev = 1.0, sigma_state = 1.0, sigma0 = 1.0;
   double atol = a.atol, rtol = a.rtol;
   double par[P];
@@ -143,19 +206,34 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
   for (;;) {
     // ---- fetch a member ----------------------------------------------------------------
     if (!have && !exhausted) {
-      unsigned long long tk = atomicAdd(a.ticket, 1ULL);
+      unsigned long long tk = 0;
+      if (sub == 0) tk = atomicAdd(a.ticket, 1ULL);
+      if (GROUP > 1) tk = __shfl_sync(gmask, tk, base);
       if (tk < (unsigned long long)a.B) {
         b = (long long)tk;
+        vb = b * DV + ((GROUP > 1 && real) ? sub : 0);
         have = true;
-        double u0[Q * D];
+        double u0[Q * DT];
 #pragma unroll
-        for (int i = 0; i < Q * D; ++i) u0[i] = a.u0[b * (Q * D) + i];
+        for (int i = 0; i < Q * DT; ++i) u0[i] = a.u0[b * (Q * DT) + i];
 #pragma unroll
         for (int i = 0; i < P; ++i) par[i] = (i < a.num_params) ? a.params[b * a.num_params + i] : 0.0;
         atol = a.tol ? a.tol[2 * b] : a.atol;
         rtol = a.tol ? a.tol[2 * b + 1] : a.rtol;
         sigma0 = a.sigma0 ? a.sigma0[b] : 1.0;
-        taylor_init<Prob, NU>(u0, par, m);
+        if constexpr (GROUP == 1) {
+          taylor_init<Prob, NU>(u0, par, m);
+        } else {
+          double tc[N][DT];
+          taylor_init<Prob, NU>(u0, par, tc);
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+            double v = tc[i][0];
+#pragma unroll
+            for (int c = 1; c < DT; ++c) v = (sub == c) ? tc[i][c] : v;
+            m[i][0] = v;
+          }
+        }
 #pragma unroll
         for (int i = 0; i < N; ++i)
 #pragma unroll
@@ -173,21 +251,21 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
         mode = MODE_STEP;
         k_next = 1;
         n_acc = n_rej = n_att = 0;
-        a.n_accepted[b * a.K] = 0;
-        if (a.flags & FLAG_RECORD) {
+        if (sub == 0) a.n_accepted[b * a.K] = 0;
+        if (GROUP == 1 && (a.flags & FLAG_RECORD)) {
           a.traj_t[b] = t;
 #pragma unroll
           for (int c = 0; c < D; ++c) a.traj_u[(long long)c * a.B + b] = m[0][c];
           a.traj_std[b] = 0.0;
         }
-        if (!FIX) {
+        if (!FIX && real) {
           // filter: slot 0 holds the initial marginal
 #pragma unroll
           for (int i = 0; i < N; ++i) {
 #pragma unroll
-            for (int c = 0; c < D; ++c) a.cond[(long long)(i * D + c) * a.B + b] = m[i][c];
+            for (int c = 0; c < D; ++c) a.cond[(long long)(i * D + c) * VB + vb] = m[i][c];
 #pragma unroll
-            for (int j = 0; j <= i; ++j) a.cond[(long long)(N * D + Lay::tri(i, j)) * a.B + b] = 0.0;
+            for (int j = 0; j <= i; ++j) a.cond[(long long)(N * D + Lay::tri(i, j)) * VB + vb] = 0.0;
           }
         }
       } else {
@@ -258,7 +336,16 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
       }
     // linearise at the predicted mean
     double z[D], h[Q + 1];
-    {
+    if (GROUP > 1) {
+      double own[Q];
+#pragma unroll
+      for (int k = 0; k < Q; ++k) own[k] = m_ext[k][0];
+      const double f_own = GroupVf<Prob, GROUP>::eval(own, sub, base, gmask, par);
+      z[0] = m_ext[Q][0] - f_own;
+#pragma unroll
+      for (int k = 0; k < Q; ++k) h[k] = 0.0;
+      h[Q] = 1.0;
+    } else {
       double uarg[Q * D], f[D];
 #pragma unroll
       for (int k = 0; k < Q; ++k)
@@ -290,9 +377,15 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
       }
       double s = dsqrt(s2);
       double zz = 0.0;
+      if (GROUP == 1) {
 #pragma unroll
-      for (int c = 0; c < D; ++c) zz = fma(z[c], z[c], zz);
-      double sigma_hat = (dsqrt(zz) * rcp(s)) * inv_sqrt_d;
+        for (int c = 0; c < D; ++c) zz = fma(z[c], z[c], zz);
+      } else {
+        zz = real ? fma(z[0], z[0], 0.0) : 0.0;
+        if (!BDIAG) zz = group_sum<GROUP>(zz, gmask);
+      }
+      double sigma_hat = dsqrt(zz) * rcp(s);
+      sigma_hat = BDIAG ? sigma_hat : sigma_hat * inv_sqrt_d;
       err = (fabs(dt) * sigma_hat) * s;
       sigma = (mode == MODE_STEP) ? ((a.calibration == 1) ? sigma_hat : sigma_given) : sigma_given;
     }
@@ -544,10 +637,15 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
 #pragma unroll
         for (int c = 0; c < D; ++c) m_new[i][c] = fma(-gain[i], z[c], m_ext[i][c]);
       double acc = 0.0;
+      if (GROUP == 1) {
 #pragma unroll
-      for (int c = 0; c < D; ++c) {
-        double ratio = err * rcp(fma(rtol, fabs(m_new[0][c]), atol));
-        acc = fma(ratio, ratio, acc);
+        for (int c = 0; c < D; ++c) {
+          double ratio = err * rcp(fma(rtol, fabs(m_new[0][c]), atol));
+          acc = fma(ratio, ratio, acc);
+        }
+      } else {
+        double ratio = err * rcp(fma(rtol, fabs(m_new[0][0]), atol));
+        acc = group_sum<GROUP>(real ? fma(ratio, ratio, 0.0) : 0.0, gmask);
       }
       e_norm = dsqrt(acc) * inv_sqrt_d;
     }
@@ -564,22 +662,24 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
     // ==================== per-lane bookkeeping (cheap, may diverge) =====================
     // helpers -------------------------------------------------------------------------
     auto ck_time = [&](long long k) { return a.save_at[k < a.K ? k : a.K - 1]; };
-    auto store_cond = [&](double* dst /* element stride a.B */) {
+    auto store_cond = [&](double* dst /* element stride VB */) {
+      if (!real) return;
 #pragma unroll
       for (int i = 0; i < N; ++i) {
 #pragma unroll
-        for (int j = 0; j < N; ++j) dst[(long long)(OFF_G + i * N + j) * a.B] = Gm[i][j];
+        for (int j = 0; j < N; ++j) dst[(long long)(OFF_G + i * N + j) * VB] = Gm[i][j];
 #pragma unroll
-        for (int c = 0; c < D; ++c) dst[(long long)(OFF_g + i * D + c) * a.B] = gm[i][c];
+        for (int c = 0; c < D; ++c) dst[(long long)(OFF_g + i * D + c) * VB] = gm[i][c];
 #pragma unroll
-        for (int j = 0; j <= i; ++j) dst[(long long)(OFF_LAM + Lay::tri(i, j)) * a.B] = Lm[i][j];
+        for (int j = 0; j <= i; ++j) dst[(long long)(OFF_LAM + Lay::tri(i, j)) * VB] = Lm[i][j];
       }
     };
     auto store_identity_cond = [&](double* dst) {
+      if (!real) return;
 #pragma unroll
-      for (int e = 0; e < Lay::BW; ++e) dst[(long long)e * a.B] = 0.0;
+      for (int e = 0; e < Lay::BW; ++e) dst[(long long)e * VB] = 0.0;
 #pragma unroll
-      for (int i = 0; i < N; ++i) dst[(long long)(OFF_G + i * N + i) * a.B] = 1.0;
+      for (int i = 0; i < N; ++i) dst[(long long)(OFF_G + i * N + i) * VB] = 1.0;
     };
     auto bw_commit = [&]() {  // running conditional <- merged result
 #pragma unroll
@@ -599,38 +699,41 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
       for (int i = 0; i < N; ++i) SBW(OFF_G + i * N + i) = 1.0;
     };
     auto store_marg = [&](double* dst, const double (&mm)[N][D], const double (&LL)[N][N]) {
+      if (!real) return;
 #pragma unroll
       for (int i = 0; i < N; ++i) {
 #pragma unroll
-        for (int c = 0; c < D; ++c) dst[(long long)(i * D + c) * a.B] = mm[i][c];
+        for (int c = 0; c < D; ++c) dst[(long long)(i * D + c) * VB] = mm[i][c];
 #pragma unroll
-        for (int j = 0; j <= i; ++j) dst[(long long)(N * D + Lay::tri(i, j)) * a.B] = LL[i][j];
+        for (int j = 0; j <= i; ++j) dst[(long long)(N * D + Lay::tri(i, j)) * VB] = LL[i][j];
       }
     };
     auto record = [&](double tt, const double (&mm)[N][D], const double (&LL)[N][N]) {
-      if ((a.flags & FLAG_RECORD) && n_acc < a.traj_cap) {
-        a.traj_t[n_acc * a.B + b] = tt;
+      if (GROUP == 1 && (a.flags & FLAG_RECORD) && n_acc < a.traj_cap) {
+        a.traj_t[n_acc * VB + vb] = tt;
 #pragma unroll
-        for (int c = 0; c < D; ++c) a.traj_u[(n_acc * D + c) * a.B + b] = mm[0][c];
-        a.traj_std[n_acc * a.B + b] = dsqrt(fma(LL[0][0], LL[0][0], 0.0));
+        for (int c = 0; c < D; ++c) a.traj_u[(n_acc * D + c) * VB + vb] = mm[0][c];
+        a.traj_std[n_acc * VB + vb] = dsqrt(fma(LL[0][0], LL[0][0], 0.0));
       }
     };
     // exact hits on checkpoints by the committed state (m, L, running conditional): emit, reset
     auto resolve_hits = [&](bool& fin) {
       while (k_next < a.K && !(t + TIME_EPS < ck_time(k_next))) {
-        double* slot = a.cond + (k_next * SLOT) * a.B + b;
+        double* slot = a.cond + (k_next * SLOT) * VB + vb;
         if (FIX) {
+          if (real) {
 #pragma unroll
-          for (int e = 0; e < Lay::BW; ++e) slot[(long long)e * a.B] = SBW(e);
+            for (int e = 0; e < Lay::BW; ++e) slot[(long long)e * VB] = SBW(e);
+          }
           if (k_next == a.K - 1) {
-            store_identity_cond(a.cond + b);
-            store_marg(a.cond + (long long)Lay::BW * a.B + b, m, L);
+            store_identity_cond(a.cond + vb);
+            store_marg(a.cond + (long long)Lay::BW * VB + vb, m, L);
           }
           bw_reset();
         } else {
           store_marg(slot, m, L);
         }
-        a.n_accepted[b * a.K + k_next] = n_acc;
+        if (sub == 0) a.n_accepted[b * a.K + k_next] = n_acc;
         k_next += 1;
       }
       if (k_next >= a.K) fin = true;
@@ -712,7 +815,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
       // prediction "previous state -> checkpoint": fixed-point emits the merged conditional
       // "t_c -> previous checkpoint" and continues from (t_c, m_t, L_t, identity); the filter emits
       // the extrapolated marginal.
-      double* slot = a.cond + (k_next * SLOT) * a.B + b;
+      double* slot = a.cond + (k_next * SLOT) * VB + vb;
       if (FIX) {
         store_cond(slot);
         bw_reset();
@@ -728,7 +831,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
 #pragma unroll
         for (int j = 0; j <= i; ++j) L[i][j] = L_ext[i][j];
       }
-      a.n_accepted[b * a.K + k_next] = n_acc;
+      if (sub == 0) a.n_accepted[b * a.K + k_next] = n_acc;
       if (FIX) {
         mode = MODE_INTERP_B;
       } else {
@@ -741,19 +844,23 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
       // model.  At the last checkpoint the terminal marginal marginalise((m1, L1), bw_1t) is
       // left to the smoothing kernel: store its two ingredients in slot 0.
       if (k_next == a.K - 1) {
-        store_cond(a.cond + b);
+        store_cond(a.cond + vb);
+        if (real) {
 #pragma unroll
-        for (int e = 0; e < Lay::MARG; ++e) a.cond[(long long)(Lay::BW + e) * a.B + b] = SPEND(2 + e);
+          for (int e = 0; e < Lay::MARG; ++e) a.cond[(long long)(Lay::BW + e) * VB + vb] = SPEND(2 + e);
+        }
       }
       k_next += 1;
       after_checkpoint(finished);
     }
     if (finished) {
-      a.n_rejected[b] = n_rej;
-      a.status[b] = st;
-      if (st != 0)
-        for (long long kk = k_next; kk < a.K; ++kk) a.n_accepted[b * a.K + kk] = n_acc;
-      if (a.flags & FLAG_RECORD) a.traj_len[b] = (n_acc + 1 < a.traj_cap) ? (n_acc + 1) : a.traj_cap;
+      if (sub == 0) {
+        a.n_rejected[b] = n_rej;
+        a.status[b] = st;
+        if (st != 0)
+          for (long long kk = k_next; kk < a.K; ++kk) a.n_accepted[b * a.K + kk] = n_acc;
+      }
+      if (GROUP == 1 && (a.flags & FLAG_RECORD)) a.traj_len[b] = (n_acc + 1 < a.traj_cap) ? (n_acc + 1) : a.traj_cap;
       have = false;
     }
   }

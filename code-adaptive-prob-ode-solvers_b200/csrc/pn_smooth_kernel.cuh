@@ -14,6 +14,8 @@ namespace pn {
 
 struct SmoothArgs {
   long long B, K;
+  int dv;              // lanes ("virtual members") per IVP: 1, or d for the lane-per-dimension kernels
+  int chol_per_dim;    // marg_chol layout: 1 -> [B][K][d][N][N] (blockdiag), 0 -> [B][K][N][N]
   const double* cond;  // [K][SLOT][B]
   const int32_t* status;
   double* u;           // [B][K][D]
@@ -94,48 +96,53 @@ __global__ void __launch_bounds__(128) pn_smooth_kernel(const SmoothArgs a) {
   using Lay = Layout<N, D>;
   constexpr bool FIX = (STRAT == 1);
   constexpr int SLOT = FIX ? Lay::SLOT_FIX : Lay::SLOT_FILT;
-  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= a.B) return;
+  // one thread per (member, owned dimension): vb = b * dv + cv; workspace stride = B * dv
+  const long long vb = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long VB = a.B * a.dv;
+  if (vb >= VB) return;
+  const long long b = vb / a.dv;
+  const int cv = (int)(vb - b * a.dv);
+  const int dtot = D * a.dv;
   const bool ok = (a.status[b] == 0);
   double m[N][D], L[N][N];
   auto load_marg = [&](const double* src) {
 #pragma unroll
     for (int i = 0; i < N; ++i) {
 #pragma unroll
-      for (int c = 0; c < D; ++c) m[i][c] = src[(long long)(i * D + c) * a.B];
+      for (int c = 0; c < D; ++c) m[i][c] = src[(long long)(i * D + c) * VB];
 #pragma unroll
-      for (int j = 0; j <= i; ++j) L[i][j] = src[(long long)(N * D + Lay::tri(i, j)) * a.B];
+      for (int j = 0; j <= i; ++j) L[i][j] = src[(long long)(N * D + Lay::tri(i, j)) * VB];
     }
   };
   if (FIX) {
     // terminal marginal = marginalise((m1, L1), bw_1t), both stored in slot 0
-    load_marg(a.cond + (long long)Lay::BW * a.B + b);
-    marginalise_from_global<N, D>(m, L, a.cond + b, a.B);
+    load_marg(a.cond + (long long)Lay::BW * VB + vb);
+    marginalise_from_global<N, D>(m, L, a.cond + vb, VB);
   }
   const double nanv = __longlong_as_double(0x7ff8000000000000LL);
   for (long long k = a.K - 1; k >= 0; --k) {
-    if (!FIX) load_marg(a.cond + (k * SLOT) * a.B + b);
+    if (!FIX) load_marg(a.cond + (k * SLOT) * VB + vb);
     const double sd = dsqrt(fma(L[0][0], L[0][0], 0.0));
 #pragma unroll
     for (int c = 0; c < D; ++c) {
-      a.u[(b * a.K + k) * D + c] = ok ? m[0][c] : nanv;
-      a.u_std[(b * a.K + k) * D + c] = ok ? sd : nanv;
+      a.u[(b * a.K + k) * dtot + cv * D + c] = ok ? m[0][c] : nanv;
+      a.u_std[(b * a.K + k) * dtot + cv * D + c] = ok ? sd : nanv;
     }
     if (a.marg_mean) {
 #pragma unroll
       for (int i = 0; i < N; ++i)
 #pragma unroll
-        for (int c = 0; c < D; ++c) a.marg_mean[((b * a.K + k) * N + i) * D + c] = ok ? m[i][c] : nanv;
+        for (int c = 0; c < D; ++c) a.marg_mean[((b * a.K + k) * N + i) * dtot + cv * D + c] = ok ? m[i][c] : nanv;
     }
-    if (a.marg_chol) {
+    if (a.marg_chol && (a.chol_per_dim || cv == 0)) {
+      const long long blk = a.chol_per_dim ? ((b * a.K + k) * a.dv + cv) : (b * a.K + k);
 #pragma unroll
       for (int i = 0; i < N; ++i)
 #pragma unroll
-        for (int j = 0; j < N; ++j)
-          a.marg_chol[((b * a.K + k) * N + i) * N + j] = ok ? ((j <= i) ? L[i][j] : 0.0) : nanv;
+        for (int j = 0; j < N; ++j) a.marg_chol[(blk * N + i) * N + j] = ok ? ((j <= i) ? L[i][j] : 0.0) : nanv;
     }
     if (k == 0) break;
-    if (FIX) marginalise_from_global<N, D>(m, L, a.cond + (k * SLOT) * a.B + b, a.B);
+    if (FIX) marginalise_from_global<N, D>(m, L, a.cond + (k * SLOT) * VB + vb, VB);
   }
 }
 

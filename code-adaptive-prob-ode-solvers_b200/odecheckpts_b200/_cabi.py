@@ -176,6 +176,14 @@ def _np_ptr(a):
     return None if a is None else C.c_void_p(a.ctypes.data)
 
 
+def _chol_shape(desc):
+    """marg_chol: [B, K, n, n] (isotropic, dense d == 1) or [B, K, d, n, n] (blockdiag)."""
+    B, K, d, n = desc.batch, desc.num_save_at, desc.d, desc.nu + 1
+    if desc.factorisation == FACTORISATIONS["blockdiag"]:
+        return (B, K, d, n, n)
+    return (B, K, n, n)
+
+
 def solve_host(desc, u0, params, tol, save_at, output_scale0, *, full=False, device=0):
     """Host-buffer entry point (numpy in, numpy out)."""
     B, K, d, n = desc.batch, desc.num_save_at, desc.d, desc.nu + 1
@@ -189,7 +197,7 @@ def solve_host(desc, u0, params, tol, save_at, output_scale0, *, full=False, dev
         "status": np.empty(B, dtype=np.int32),
     }
     mm = np.empty((B, K, n, d)) if full else None
-    mc = np.empty((B, K, n, n)) if full else None
+    mc = np.empty(_chol_shape(desc)) if full else None
     rec = bool(desc.flags & FLAG_RECORD)
     cap = desc.traj_capacity
     tt = np.empty((cap, B)) if rec else None
@@ -241,7 +249,7 @@ def solve_device(desc, u0, params, tol, save_at, output_scale0, *, full=False, w
         }
         if full:
             out["marg_mean"] = torch.empty((B, K, n, d), **f64)
-            out["marg_chol"] = torch.empty((B, K, n, n), **f64)
+            out["marg_chol"] = torch.empty(_chol_shape(desc), **f64)
         if desc.flags & FLAG_RECORD:
             cap = desc.traj_capacity
             out["traj_t"] = torch.empty((cap, B), **f64)

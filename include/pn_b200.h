@@ -82,7 +82,8 @@ size_t pn_b200_workspace_bytes(const pn_b200_desc* desc);
  *   save_at       [K]           checkpoints, strictly increasing, save_at[0] = t0
  *   output_scale0 [B] | NULL    initial output scale (ivpsolvers.py:55,68); NULL: 1.0
  *   u, u_std      [B][K][d]     smoothed checkpoint means / marginal standard deviations
- *   marg_mean     [B][K][n][d] | NULL, marg_chol [B][K][n][n] | NULL   full marginals (n = nu+1)
+ *   marg_mean     [B][K][n][d] | NULL, marg_chol [B][K][n][n] | NULL   full marginals (n = nu+1);
+ *                 blockdiag with d > 1: marg_chol is [B][K][d][n][n] (one factor per dimension)
  *   n_accepted    [B][K]        cumulative accepted steps when checkpoint k was emitted
  *   n_rejected    [B], status [B]
  *   traj_*        PN_B200_FLAG_RECORD only: traj_t [cap][B], traj_u [cap][d][B], traj_std [cap][B],

@@ -73,7 +73,12 @@ typedef struct {
   double safety, factor_min, factor_max, power_integral, power_proportional;
   int64_t max_attempts;  /* per member; <=0: unlimited                            */
   int32_t num_params;
-  int32_t reserved;
+  /* Summation order of the two norms over the ODE dimensions (||z|| for the isotropic calibration
+   * and the scaled error norm).  <= 1: ascending-index fma chain (what a thread-per-IVP kernel
+   * does).  G > 1 (power of two >= d): one square per lane, then a butterfly (xor 2^k) sum over G
+   * lanes with zero padding -- the order the lane-per-dimension CUDA kernels use.  Any order is a
+   * faithful restatement; this knob only exists so that comparisons can be bit-exact. */
+  int32_t reduction_group;
 } pn_oracle_config;
 
 /* ---- deterministic elementary functions (shared contract with the kernel) ---- */

@@ -49,7 +49,7 @@ class Config(C.Structure):
         ("power_proportional", C.c_double),
         ("max_attempts", C.c_int64),
         ("num_params", C.c_int32),
-        ("reserved", C.c_int32),
+        ("reduction_group", C.c_int32),
     ]
 
 
@@ -113,6 +113,7 @@ def make_config(
     factor_max=10.0,
     power_integral=0.3,
     power_proportional=0.4,
+    reduction_group=0,
 ):
     return Config(
         PROBLEMS[problem] if isinstance(problem, str) else int(problem),
@@ -133,7 +134,7 @@ def make_config(
         power_proportional,
         int(max_attempts),
         int(num_params),
-        0,
+        int(reduction_group),
     )
 
 

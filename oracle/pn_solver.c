@@ -228,6 +228,23 @@ static void precondition(const engine *E, double dt, double *p, double *pinv) {
   }
 }
 
+/* sum of squares of v[0..k) in the configured order (see pn_oracle_config.reduction_group) */
+static double sum_squares(const engine *E, const double *v, int k) {
+  int G = E->cfg.reduction_group;
+  if (G <= 1) {
+    double acc = 0.0;
+    for (int c = 0; c < k; ++c) acc = fma(v[c], v[c], acc);
+    return acc;
+  }
+  double lanes[64], next[64];
+  for (int l = 0; l < G; ++l) lanes[l] = (l < k) ? fma(v[l], v[l], 0.0) : 0.0;
+  for (int off = G / 2; off >= 1; off >>= 1) {
+    for (int l = 0; l < G; ++l) next[l] = lanes[l] + lanes[l ^ off];
+    for (int l = 0; l < G; ++l) lanes[l] = next[l];
+  }
+  return lanes[0];
+}
+
 /* predicted mean: m_p = pinv*m, m_ext_p = A m_p, m_ext = p*m_ext_p */
 static void predict_mean(engine *E, const double *mean) {
   int N = E->N, Ct = E->Ctot;
@@ -407,8 +424,7 @@ static void calibrate_and_estimate(engine *E, double dt) {
     double s = sqrt(s2);
     for (int f = 0; f < E->F; ++f) {
       int c0 = f * E->C;
-      double zz = 0.0;
-      for (int c = c0; c < c0 + E->C; ++c) zz = fma(E->z[c], E->z[c], zz);
+      double zz = sum_squares(E, E->z + c0, E->C);
       double sigma_hat = (sqrt(zz) * (1.0 / s)) * E->inv_sqrt_C;
       E->sig[f] = sigma_hat;
       double er = (adt * sigma_hat) * s;
@@ -553,11 +569,8 @@ static void attempt_step(engine *E, const double *params, const pstate *S, doubl
   }
   P->t = S->t + dt;
   /* scaled error norm: uses the PROPOSED u only (App. A.3, quirk confirmed against the golden) */
-  double acc = 0.0;
-  for (int l = 0; l < d; ++l) {
-    double ratio = E->err[l] * (1.0 / fma(rtol, fabs(P->mean[l]), atol));
-    acc = fma(ratio, ratio, acc);
-  }
+  for (int l = 0; l < d; ++l) E->fbuf[l] = E->err[l] * (1.0 / fma(rtol, fabs(P->mean[l]), atol));
+  double acc = sum_squares(E, E->fbuf, d);
   double e = sqrt(acc) * E->inv_sqrt_d;
   info->error_norm = e;
   info->dt_proposed = pi_factor(E, e, e_prev) * dt;

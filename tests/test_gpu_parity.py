@@ -35,6 +35,7 @@ def _desc(cabi, problem, d, nu, q, B, K, *, fact="isotropic", corr="ts0", strat=
 
 def _ocfg(oracle, problem, d, nu, q, **kw):
     m = dict(fact="factorisation", corr="correction", strat="strategy", calib="calibration", P="num_params")
+    kw = {k: v for k, v in kw.items() if k not in ("flags", "cap")}
     kw2 = {m.get(k, k): v for k, v in kw.items()}
     return oracle.make_config(problem, d, nu, q, **kw2)
 
@@ -212,3 +213,61 @@ def test_device_pointer_entry_and_public_api(cabi, oracle):
     np.testing.assert_array_equal(sol_d.cpu().numpy(), ora["u"])
     with pytest.raises(ValueError, match="Tuple expected."):
         solve(u0[0], args)
+
+
+# ---- lane-per-dimension kernels (blockdiag, and isotropic for d = 14) ------------------------------
+GROUP_CASES = [
+    # problem, d, nu, q, P, params, u0 fn, save_at, group, kwargs
+    ("pleiades", 14, 3, 2, 0, (), pu.pleiades_u0, np.linspace(0, 3, 50), 16, dict(atol=1e-7, rtol=1e-4, dt0=0.1, fact="isotropic")),
+    ("pleiades", 14, 5, 2, 0, (), pu.pleiades_u0, np.linspace(0, 3, 50), 16, dict(atol=1e-9, rtol=1e-6, dt0=0.1, fact="isotropic")),
+    ("pleiades", 14, 3, 2, 0, (), pu.pleiades_u0, np.linspace(0, 3, 50), 16, dict(atol=1e-7, rtol=1e-4, dt0=0.1, fact="blockdiag")),
+    ("pleiades", 14, 4, 2, 0, (), pu.pleiades_u0, np.linspace(0, 3, 50), 16, dict(atol=1e-8, rtol=1e-5, dt0=0.1, fact="blockdiag")),
+    ("pleiades", 14, 5, 2, 0, (), pu.pleiades_u0, np.linspace(0, 3, 50), 16, dict(atol=1e-9, rtol=1e-6, dt0=0.1, fact="blockdiag", calib="none")),
+    ("rigid_body", 3, 4, 1, 3, pu.RIGID_BODY_PARAMS, pu.rigid_body_u0, np.linspace(0, 50, 5), 4, dict(atol=1e-9, rtol=1e-6, dt0=50.0, fact="blockdiag")),
+    ("three_body", 2, 4, 2, 1, (pu.THREE_BODY_MU,), pu.three_body_u0, np.linspace(0, pu.THREE_BODY_T, 50), 2, dict(atol=1e-7, rtol=1e-7, fact="blockdiag")),
+    ("lotka_volterra", 2, 4, 1, 4, (0.5, 0.05, 0.5, 0.05), lambda: np.array([[20.0, 20.0]]), np.linspace(0, 20, 30), 2, dict(atol=1e-6, rtol=1e-6, dt0=0.1, fact="blockdiag")),
+]
+
+
+@pytest.mark.parametrize("case", GROUP_CASES, ids=lambda c: f"{c[0]}-nu{c[2]}-{c[9]['fact']}")
+def test_lane_per_dimension_kernels_bitwise_vs_oracle(cabi, oracle, case):
+    problem, d, nu, q, P, params, u0fn, save_at, group, kw = case
+    kw = dict(kw, P=P)
+    u0 = u0fn()
+    K = len(save_at)
+    B = 5  # members share a warp with others: perturb the initial values
+    rng = np.random.default_rng(7)
+    u0_b = u0[None] * (1.0 + 1e-3 * rng.standard_normal((B,) + u0.shape))
+    u0_b[0] = u0
+    par_b = np.tile(np.asarray(params, dtype=float), (B, 1)) if P else None
+    desc = _desc(cabi, problem, d, nu, q, B, K, **kw)
+    gpu = cabi.solve_host(desc, u0_b, par_b, None, save_at, None, full=True)
+    ocfg = _ocfg(oracle, problem, d, nu, q, reduction_group=group, **kw)
+    for b in range(B):
+        ora = oracle.solve_save_at(ocfg, u0_b[b], params, save_at, full=True)
+        assert ora["status"] == 0
+        _assert_bitwise({k: v[b] for k, v in gpu.items()}, ora)
+        np.testing.assert_array_equal(gpu["marg_mean"][b].reshape(K, -1), ora["marg_mean"].reshape(K, -1))
+        np.testing.assert_array_equal(gpu["marg_chol"][b].reshape(K, -1), ora["marg_chol"].reshape(K, -1))
+
+
+def test_pleiades_golden_checkpoint_rmse_on_gpu(cabi, oracle, goldens):
+    # experiments/3_workprec_harder/run_harder.py:42-60 (isotropic EKF0, ode_order=2, 50 checkpoints)
+    import scipy.integrate
+
+    xs = goldens["pleiades_checkpoints"]
+    y0 = pu.pleiades_u0()
+
+    def f(t, y):
+        return np.concatenate([y[14:], oracle.vf("pleiades", y.reshape(2, -1), [])])
+
+    ref = scipy.integrate.solve_ivp(f, (xs[0], xs[-1]), y0.ravel(), t_eval=xs, method="DOP853", atol=1e-13, rtol=1e-13).y.T[:, :14]
+    for nu, key in [(3, "pleiades_nu3"), (5, "pleiades_nu5")]:
+        tols = goldens[key + "_list_of_args"][:5] * 10  # run_harder.py:45-47
+        B = len(tols)
+        tol = np.stack([1e-3 * tols, tols], 1)
+        desc = _desc(cabi, "pleiades", 14, nu, 2, B, len(xs), dt0=0.1)
+        gpu = cabi.solve_host(desc, np.tile(y0[None], (B, 1, 1)), None, tol, xs, None)
+        assert (gpu["status"] == 0).all()
+        rmse = np.linalg.norm((gpu["u"] - ref[None]).reshape(B, -1), axis=1) / np.sqrt(ref.size)
+        np.testing.assert_allclose(rmse, goldens[key + "_precision"][:5], rtol=1e-3)
