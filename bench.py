@@ -55,10 +55,9 @@ def ensemble_inputs(first, count, stride=1):
     """Members first, first+stride, ... of the seeded global ensemble (seed 0)."""
     total = first + stride * count
     rng = np.random.default_rng(0)
-    a = rng.uniform(-1, 1, total)
-    b = rng.uniform(-1, 1, total)
+    ab = rng.uniform(-1, 1, (total, 2))  # row b = member b, whatever the ensemble size
     idx = first + stride * np.arange(count)
-    u0 = np.stack([2.0 + 0.5 * a[idx], 0.5 * b[idx]], 1).reshape(count, 2, 1)
+    u0 = np.stack([2.0 + 0.5 * ab[idx, 0], 0.5 * ab[idx, 1]], 1).reshape(count, 2, 1)
     params = np.full((count, 1), MU)
     return np.ascontiguousarray(u0), params
 
