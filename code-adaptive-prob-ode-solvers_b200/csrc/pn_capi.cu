@@ -22,9 +22,9 @@ static std::vector<KernelEntry>& table() {
   return t;
 }
 void register_kernel(const KernelEntry& e) { table().push_back(e); }
-const KernelEntry* find_kernel(int family, int problem, int nu, int strategy) {
+const KernelEntry* find_kernel(int family, int problem, int nu, int strategy, int d) {
   for (const auto& e : table())
-    if (e.family == family && e.problem == problem && e.nu == nu && e.strategy == strategy) return &e;
+    if (e.family == family && e.problem == problem && e.nu == nu && e.strategy == strategy && e.D == d) return &e;
   return nullptr;
 }
 
@@ -92,12 +92,15 @@ static int resolve(const pn_b200_desc* d, const KernelEntry** out) {
   bool scalar_ok = (d->factorisation == PN_B200_ISOTROPIC && d->correction == PN_B200_TS0) ||
                    (d->factorisation == PN_B200_DENSE && d->d == 1) ||
                    (d->factorisation == PN_B200_BLOCKDIAG && d->d == 1 && d->correction == PN_B200_TS0);
-  if (scalar_ok) k = find_kernel(FAMILY_SCALAR, d->problem, d->nu, d->strategy);
+  if (scalar_ok) k = find_kernel(FAMILY_SCALAR, d->problem, d->nu, d->strategy, d->d);
   // lane-per-dimension family: blockdiag EKF0, and isotropic EKF0 for problems too wide for one thread
   if (!k && d->correction == PN_B200_TS0 && d->factorisation == PN_B200_BLOCKDIAG)
-    k = find_kernel(FAMILY_GROUP_BDIAG, d->problem, d->nu, d->strategy);
+    k = find_kernel(FAMILY_GROUP_BDIAG, d->problem, d->nu, d->strategy, d->d);
   if (!k && d->correction == PN_B200_TS0 && d->factorisation == PN_B200_ISOTROPIC)
-    k = find_kernel(FAMILY_GROUP_ISO, d->problem, d->nu, d->strategy);
+    k = find_kernel(FAMILY_GROUP_ISO, d->problem, d->nu, d->strategy, d->d);
+  // warp-per-IVP dense family: dense factorisation with d > 1, EKF0 or EKF1
+  if (!k && d->factorisation == PN_B200_DENSE && d->d > 1)
+    k = find_kernel(FAMILY_DENSE, d->problem, d->nu, d->strategy, d->d);
   if (k && k->group > 1 && (d->flags & PN_B200_FLAG_RECORD))
     return fail(PN_B200_ERR_UNSUPPORTED, "trajectory recording is implemented for the thread-per-IVP kernels");
   if (!k) {
@@ -106,7 +109,7 @@ static int resolve(const pn_b200_desc* d, const KernelEntry** out) {
              d->problem, d->nu, d->factorisation, d->correction, d->strategy, d->d);
     return fail(PN_B200_ERR_UNSUPPORTED, buf);
   }
-  if (k->D != d->d || k->Q != d->ode_order) return fail(PN_B200_ERR_ARGUMENT, "d / ode_order do not match the problem");
+  if (k->Q != d->ode_order) return fail(PN_B200_ERR_ARGUMENT, "ode_order does not match the problem");
   if (d->correction == PN_B200_TS1 && !k->has_jac) return fail(PN_B200_ERR_UNSUPPORTED, "problem has no compiled Jacobian");
   if (d->num_params < 0 || d->num_params > (k->P > 0 ? k->P : 0)) return fail(PN_B200_ERR_ARGUMENT, "num_params exceeds the problem's parameter count");
   *out = k;
@@ -116,7 +119,9 @@ static int resolve(const pn_b200_desc* d, const KernelEntry** out) {
 static int make_plan(const pn_b200_desc* d, Plan* p, bool need_device) {
   int rc = resolve(d, &p->k);
   if (rc) return rc;
-  p->smem = (size_t)p->k->smem_doubles * p->k->threads * sizeof(double);
+  p->smem = (p->k->family == FAMILY_DENSE)
+                ? (size_t)p->k->smem_doubles * (p->k->threads / 32) * sizeof(double)  // per warp
+                : (size_t)p->k->smem_doubles * p->k->threads * sizeof(double);        // per thread
   p->ws_cond = (size_t)d->num_save_at * p->k->slot_doubles * (size_t)d->batch * p->k->dv * sizeof(double);
   if (!need_device) return PN_B200_SUCCESS;
   int dev = 0;
@@ -353,7 +358,8 @@ int pn_b200_solve_save_at_host(const pn_b200_desc* desc, const double* u0, const
       {&d_u, nullptr, u, B * K * d * 8},
       {&d_std, nullptr, u_std, B * K * d * 8},
       {&d_mm, nullptr, marg_mean, marg_mean ? B * K * n * d * 8 : 0},
-      {&d_mc, nullptr, marg_chol, marg_chol ? B * K * (k->family == FAMILY_GROUP_BDIAG ? d : 1) * n * n * 8 : 0},
+      {&d_mc, nullptr, marg_chol,
+       marg_chol ? B * K * (k->family == FAMILY_GROUP_BDIAG ? d : (k->family == FAMILY_DENSE ? d * d : 1)) * n * n * 8 : 0},
       {&d_nacc, nullptr, n_accepted, B * K * 8},
       {&d_nrej, nullptr, n_rejected, B * 8},
       {&d_stat, nullptr, status, B * 4},

@@ -249,6 +249,72 @@ struct Pleiades {
   }
 };
 
+// ---- Brusselator with N grid points, d = 2N (ivps.py:124-156); params (alpha) ---------------
+// u = (u[N], v[N]); boundary pads u = 1, v = 3; c = alpha (N+1)^2.  Fixed small N only (lane per
+// dimension); large N runs in the warp-per-IVP kernel (pn_wide_kernel.cuh).
+template <int NPTS>
+struct Brusselator {
+  static constexpr int D = 2 * NPTS, Q = 1, P = 1, ID = 4;
+  static constexpr bool HAS_JAC = true;
+  PN_DEV static void vf(const double* u, const double* par, double* f) {
+    const double c = par[0] * (double)((NPTS + 1) * (NPTS + 1));
+    const double *uu = u, *vv = u + NPTS;
+#pragma unroll
+    for (int i = 0; i < NPTS; ++i) {
+      double ul = (i == 0) ? 1.0 : uu[i - 1], ur = (i == NPTS - 1) ? 1.0 : uu[i + 1];
+      double vl = (i == 0) ? 3.0 : vv[i - 1], vr = (i == NPTS - 1) ? 3.0 : vv[i + 1];
+      double uuv = (uu[i] * uu[i]) * vv[i];
+      double lap_u = fma(-2.0, uu[i], ul + ur);
+      double lap_v = fma(-2.0, vv[i], vl + vr);
+      f[i] = fma(c, lap_u, fma(-4.0, uu[i], 1.0 + uuv));
+      f[NPTS + i] = fma(c, lap_v, fma(3.0, uu[i], -uuv));
+    }
+  }
+  PN_DEV static void jac(const double* u, const double* par, double* J) {
+    const double c = par[0] * (double)((NPTS + 1) * (NPTS + 1));
+    const double *uu = u, *vv = u + NPTS;
+    for (int e = 0; e < D * D; ++e) J[e] = 0.0;
+    for (int i = 0; i < NPTS; ++i) {
+      const double two_uv = (2.0 * uu[i]) * vv[i];
+      const double u2 = uu[i] * uu[i];
+      J[i * D + i] = fma(-2.0, c, two_uv - 4.0);
+      J[i * D + NPTS + i] = u2;
+      J[(NPTS + i) * D + i] = 3.0 - two_uv;
+      J[(NPTS + i) * D + NPTS + i] = fma(-2.0, c, -u2);
+      if (i > 0) {
+        J[i * D + i - 1] = c;
+        J[(NPTS + i) * D + NPTS + i - 1] = c;
+      }
+      if (i < NPTS - 1) {
+        J[i * D + i + 1] = c;
+        J[(NPTS + i) * D + NPTS + i + 1] = c;
+      }
+    }
+  }
+  template <int N>
+  PN_DEV static void vf_jet(const double* U, const double* par, double* F) {
+    const double c = par[0] * (double)((NPTS + 1) * (NPTS + 1));
+    for (int i = 0; i < NPTS; ++i) {
+      const double* ui = U + i * N;
+      const double* vi = U + (NPTS + i) * N;
+      double u2[N], uuv[N];
+      jet_mul<N>(ui, ui, u2);
+      jet_mul<N>(u2, vi, uuv);
+      for (int k = 0; k < N; ++k) {
+        double padu = (k == 0) ? 1.0 : 0.0, padv = (k == 0) ? 3.0 : 0.0;
+        double ul = (i == 0) ? padu : U[(i - 1) * N + k];
+        double ur = (i == NPTS - 1) ? padu : U[(i + 1) * N + k];
+        double vl = (i == 0) ? padv : U[(NPTS + i - 1) * N + k];
+        double vr = (i == NPTS - 1) ? padv : U[(NPTS + i + 1) * N + k];
+        double lap_u = fma(-2.0, ui[k], ul + ur);
+        double lap_v = fma(-2.0, vi[k], vl + vr);
+        F[i * N + k] = fma(c, lap_u, fma(-4.0, ui[k], padu + uuv[k]));
+        F[(NPTS + i) * N + k] = fma(c, lap_v, fma(3.0, ui[k], -uuv[k]));
+      }
+    }
+  }
+};
+
 // taylor.odejet_padded_scan replacement: tc[k][l] = u_l^{(k)}(t0), k = 0..NU.
 template <class Prob, int NU>
 PN_DEV void taylor_init(const double* u0 /*[Q*D]*/, const double* par, double (&tc)[NU + 1][Prob::D]) {

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "pn_dense_kernel.cuh"
 #include "pn_scalar_kernel.cuh"
 #include "pn_smooth_kernel.cuh"
 
@@ -10,7 +11,8 @@ namespace pn {
 enum : int {
   FAMILY_SCALAR = 0,      // thread per IVP, one n x n factor shared by all mean columns
   FAMILY_GROUP_ISO = 1,   // lane per dimension, identical factors (isotropic)
-  FAMILY_GROUP_BDIAG = 2  // lane per dimension, per-dimension factors (blockdiag)
+  FAMILY_GROUP_BDIAG = 2, // lane per dimension, per-dimension factors (blockdiag)
+  FAMILY_DENSE = 3        // warp per IVP, D x D factors in shared memory (dense, d > 1)
 };
 
 struct KernelEntry {
@@ -28,7 +30,7 @@ struct KernelEntry {
 };
 
 void register_kernel(const KernelEntry& e);
-const KernelEntry* find_kernel(int family, int problem, int nu, int strategy);
+const KernelEntry* find_kernel(int family, int problem, int nu, int strategy, int d);
 
 template <class Prob, int NU, int STRAT, int GROUP, int BDIAG, int THREADS>
 struct ScalarInstance {
@@ -67,6 +69,46 @@ struct ScalarInstance {
   }
 };
 
+// dense factorisation with d > 1: warp per IVP
+template <class Prob, int NU, int STRAT, int WARPS>
+struct DenseInstance {
+  using Lay = DenseLayout<NU + 1, Prob::D>;
+  static cudaError_t launch_solve(const SolveArgs& a, int grid, size_t smem, cudaStream_t s) {
+    pn_dense_kernel<Prob, NU, STRAT, WARPS><<<grid, 32 * WARPS, smem, s>>>(a);
+    return cudaGetLastError();
+  }
+  static cudaError_t launch_smooth(const SmoothArgs& a, cudaStream_t s) {
+    const size_t smem = (size_t)WARPS * Lay::SMEM_SMOOTH * sizeof(double);
+    auto kern = pn_dense_smooth_kernel<NU + 1, Prob::D, STRAT, WARPS>;
+    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ce != cudaSuccess) return ce;
+    int grid = (int)((a.B + WARPS - 1) / WARPS);
+    kern<<<grid, 32 * WARPS, smem, s>>>(a);
+    return cudaGetLastError();
+  }
+  static KernelEntry entry() {
+    KernelEntry e;
+    e.family = FAMILY_DENSE;
+    e.group = 32;
+    e.dv = 1;
+    e.problem = Prob::ID;
+    e.nu = NU;
+    e.strategy = STRAT;
+    e.N = NU + 1;
+    e.D = Prob::D;
+    e.Q = Prob::Q;
+    e.P = Prob::P;
+    e.slot_doubles = (STRAT == 1) ? Lay::SLOT_FIX : Lay::SLOT_FILT;
+    e.smem_doubles = Lay::SMEM;  // per warp (= per 32 threads), see make_plan
+    e.threads = 32 * WARPS;
+    e.has_jac = Prob::HAS_JAC;
+    e.solve_func = (const void*)&pn_dense_kernel<Prob, NU, STRAT, WARPS>;
+    e.launch_solve = &launch_solve;
+    e.launch_smooth = &launch_smooth;
+    return e;
+  }
+};
+
 struct Registrar {
   explicit Registrar(const KernelEntry& e) { register_kernel(e); }
 };
@@ -75,6 +117,8 @@ struct Registrar {
 #define PN_CAT(a, b) PN_CAT2(a, b)
 #define PN_REGISTER_SCALAR(Prob, NU, STRAT) \
   static ::pn::Registrar PN_CAT(pn_reg_, __COUNTER__)(::pn::ScalarInstance<::pn::Prob, NU, STRAT, 1, 0, 128>::entry())
+#define PN_REGISTER_DENSE(Prob, NU, STRAT, WARPS) \
+  static ::pn::Registrar PN_CAT(pn_reg_, __COUNTER__)(::pn::DenseInstance<::pn::Prob, NU, STRAT, WARPS>::entry())
 // lane-per-dimension kernels: GROUP lanes per IVP, BDIAG = 1 blockdiag / 0 isotropic
 #define PN_REGISTER_GROUP(Prob, NU, STRAT, GROUP, BDIAG) \
   static ::pn::Registrar PN_CAT(pn_reg_, __COUNTER__)(::pn::ScalarInstance<::pn::Prob, NU, STRAT, GROUP, BDIAG, 128>::entry())

@@ -152,6 +152,27 @@ struct GroupVf<Pleiades, GROUP> {
   }
 };
 
+// Brusselator: lane i < N owns u_i, lane N + i owns v_i; nearest-neighbour stencil by shuffles.
+template <int NPTS, int GROUP>
+struct GroupVf<Brusselator<NPTS>, GROUP> {
+  PN_DEV static double eval(const double* own, int sub, int base, unsigned gmask, const double* par) {
+    const bool isu = sub < NPTS;
+    const int i = isu ? sub : sub - NPTS;
+    const double c = par[0] * (double)((NPTS + 1) * (NPTS + 1));
+    const double me = own[0];
+    const double lft = __shfl_sync(gmask, me, base + ((sub > 0) ? sub - 1 : 0));
+    const double rgt = __shfl_sync(gmask, me, base + ((sub + 1 < GROUP) ? sub + 1 : GROUP - 1));
+    const double oth = __shfl_sync(gmask, me, base + (isu ? ((sub + NPTS < GROUP) ? sub + NPTS : sub) : sub - NPTS));
+    const double pad = isu ? 1.0 : 3.0;
+    const double l = (i == 0) ? pad : lft;
+    const double r = (i == NPTS - 1) ? pad : rgt;
+    const double ui = isu ? me : oth, vi = isu ? oth : me;
+    const double uuv = (ui * ui) * vi;
+    const double lap = fma(-2.0, me, l + r);
+    return isu ? fma(c, lap, fma(-4.0, ui, 1.0 + uuv)) : fma(c, lap, fma(3.0, ui, -uuv));
+  }
+};
+
 #ifndef PN_MINBLOCKS
 #define PN_MINBLOCKS 2
 #endif

@@ -177,10 +177,13 @@ def _np_ptr(a):
 
 
 def _chol_shape(desc):
-    """marg_chol: [B, K, n, n] (isotropic, dense d == 1) or [B, K, d, n, n] (blockdiag)."""
+    """marg_chol: [B, K, n, n] (isotropic, dense d == 1), [B, K, d, n, n] (blockdiag) or
+    [B, K, D, D] (dense, D = n d, derivative-major)."""
     B, K, d, n = desc.batch, desc.num_save_at, desc.d, desc.nu + 1
     if desc.factorisation == FACTORISATIONS["blockdiag"]:
         return (B, K, d, n, n)
+    if desc.factorisation == FACTORISATIONS["dense"] and d > 1:
+        return (B, K, n * d, n * d)
     return (B, K, n, n)
 
 
