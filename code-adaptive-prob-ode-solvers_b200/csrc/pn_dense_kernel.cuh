@@ -54,8 +54,9 @@ PN_DEV void qr_r(double* M, int ld, int rows, int cols, int lane) {
     const double beta = (alpha >= 0.0) ? -norm : norm;
     const double g = rcp(norm * (fabs(alpha) + norm));
     for (int c = j + 1 + lane; c < cols; c += 32) {
-      double w = v0 * M[j * ld + c];
+      double w = 0.0;
       for (int i = j + 1; i < rows; ++i) w = fma(M[i * ld + j], M[i * ld + c], w);
+      w = fma(v0, M[j * ld + c], w);
       const double f = w * g;
       M[j * ld + c] = fma(-f, v0, M[j * ld + c]);
       for (int i = j + 1; i < rows; ++i) M[i * ld + c] = fma(-f, M[i * ld + j], M[i * ld + c]);

@@ -59,7 +59,7 @@ struct ScalarInstance {
     e.Q = Prob::Q;
     e.P = Prob::P;
     e.slot_doubles = (STRAT == 1) ? Lay::SLOT_FIX : Lay::SLOT_FILT;
-    e.smem_doubles = ((STRAT == 1) ? Lay::BW : 0) + Lay::PEND;
+    e.smem_doubles = ((STRAT == 1) ? Lay::BW : 0) + Lay::PEND + Lay::MARG;
     e.threads = THREADS;
     e.has_jac = Prob::HAS_JAC;
     e.solve_func = (const void*)&pn_scalar_kernel<Prob, NU, STRAT, GROUP, BDIAG, THREADS>;

@@ -195,9 +195,12 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
   // [element][thread]
   double* s_bw = smem;                                       // BW * THREADS (fixed-point only)
   double* s_pend = smem + (FIX ? Lay::BW : 0) * THREADS;     // PEND * THREADS
+  double* s_state = s_pend + Lay::PEND * THREADS;            // MARG * THREADS: hidden state (mean, factor)
   const int tid = threadIdx.x;
 #define SBW(e) s_bw[(e) * THREADS + tid]
 #define SPEND(e) s_pend[(e) * THREADS + tid]
+#define SM(i, c) s_state[((i) * D + (c)) * THREADS + tid]
+#define SL(i, j) s_state[(N * D + Lay::tri(i, j)) * THREADS + tid]
   constexpr int OFF_G = 0, OFF_g = N * N, OFF_LAM = N * N + N * D;
 
   const double* LQ = a.lq;
@@ -215,8 +218,6 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
   double t = 0.0, dt_next = 0.0, e_prev = 1.0, sigma_state = 1.0, sigma0 = 1.0;
   double atol = a.atol, rtol = a.rtol;
   double par[P];
-  double m[N][D];
-  double L[N][N];  // lower triangle used
   int mode = MODE_STEP;
   long long k_next = 1, n_acc = 0, n_rej = 0, n_att = 0;
   // utilisation statistics (per warp, flushed once at exit): loop iterations, lane-iterations with
@@ -242,23 +243,26 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
         atol = a.tol ? a.tol[2 * b] : a.atol;
         rtol = a.tol ? a.tol[2 * b + 1] : a.rtol;
         sigma0 = a.sigma0 ? a.sigma0[b] : 1.0;
-        if constexpr (GROUP == 1) {
-          taylor_init<Prob, NU>(u0, par, m);
-        } else {
+        {
           double tc[N][DT];
           taylor_init<Prob, NU>(u0, par, tc);
 #pragma unroll
           for (int i = 0; i < N; ++i) {
-            double v = tc[i][0];
+            if constexpr (GROUP == 1) {
 #pragma unroll
-            for (int c = 1; c < DT; ++c) v = (sub == c) ? tc[i][c] : v;
-            m[i][0] = v;
+              for (int c = 0; c < D; ++c) SM(i, c) = tc[i][c];
+            } else {
+              double v = tc[i][0];
+#pragma unroll
+              for (int c = 1; c < DT; ++c) v = (sub == c) ? tc[i][c] : v;
+              SM(i, 0) = v;
+            }
           }
         }
 #pragma unroll
         for (int i = 0; i < N; ++i)
 #pragma unroll
-          for (int j = 0; j <= i; ++j) L[i][j] = 0.0;
+          for (int j = 0; j <= i; ++j) SL(i, j) = 0.0;
         if (FIX) {
 #pragma unroll
           for (int e = 0; e < Lay::BW; ++e) SBW(e) = 0.0;
@@ -276,7 +280,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
         if (GROUP == 1 && (a.flags & FLAG_RECORD)) {
           a.traj_t[b] = t;
 #pragma unroll
-          for (int c = 0; c < D; ++c) a.traj_u[(long long)c * a.B + b] = m[0][c];
+          for (int c = 0; c < D; ++c) a.traj_u[(long long)c * a.B + b] = SM(0, c);
           a.traj_std[b] = 0.0;
         }
         if (!FIX && real) {
@@ -284,7 +288,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
 #pragma unroll
           for (int i = 0; i < N; ++i) {
 #pragma unroll
-            for (int c = 0; c < D; ++c) a.cond[(long long)(i * D + c) * VB + vb] = m[i][c];
+            for (int c = 0; c < D; ++c) a.cond[(long long)(i * D + c) * VB + vb] = SM(i, c);
 #pragma unroll
             for (int j = 0; j <= i; ++j) a.cond[(long long)(N * D + Lay::tri(i, j)) * VB + vb] = 0.0;
           }
@@ -344,7 +348,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
 #pragma unroll
     for (int i = 0; i < N; ++i)
 #pragma unroll
-      for (int c = 0; c < D; ++c) m_p[i][c] = pinv[i] * m[i][c];
+      for (int c = 0; c < D; ++c) m_p[i][c] = pinv[i] * SM(i, c);
 #pragma unroll
     for (int i = 0; i < N; ++i)
 #pragma unroll
@@ -414,12 +418,15 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
     double L_ext[N][N];         // lower
     double Gn[N][N], gn[N][D];  // new conditional (un-preconditioned); Lam_n lower
     double Ln[N][N];
+    double RY[N][N];   // upper
+    double R12[N][N];  // full (fixed-point)
+    double BR[N][N];   // bottom-right block, starts as L_p^T (upper), fills in (fixed-point)
     {
       double L_p[N][N];  // lower
 #pragma unroll
       for (int i = 0; i < N; ++i)
 #pragma unroll
-        for (int j = 0; j <= i; ++j) L_p[i][j] = pinv[i] * L[i][j];
+        for (int j = 0; j <= i; ++j) L_p[i][j] = pinv[i] * SL(i, j);
       // BL[i][j] = (A L_p)[j][i]
       double BL[N][N];
 #pragma unroll
@@ -433,56 +440,147 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
           BL[j][i] = acc;
         }
       // top-left block rows: TL[j][c] = sigma * LQ[c][j] (c >= j), materialised when row j is used
-      double RY[N][N];   // upper
-      double R12[N][N];  // full (fixed-point)
-      double BR[N][N];   // bottom-right block, starts as L_p^T (upper), fills in (fixed-point)
       if (FIX) {
 #pragma unroll
         for (int i = 0; i < N; ++i)
 #pragma unroll
           for (int c = 0; c < N; ++c) BR[i][c] = (i <= c) ? L_p[c][i] : 0.0;
       }
-#pragma unroll
-      for (int j = 0; j < N; ++j) {
+      // Phase 1 with look-ahead: reflector j+1 only needs left column j+1, so that column is updated
+      // first and the next reflector's serial chain (norm -> sqrt -> reciprocal) is issued BEFORE the
+      // bulk of reflector j's trailing updates, which ptxas then overlaps with it.  Same arithmetic
+      // per value as the plain column-by-column loop.
+      auto column_reflector = [&](int j) {
         double sigma2 = 0.0;
 #pragma unroll
         for (int i = 0; i < N; ++i) sigma2 = fma(BL[i][j], BL[i][j], sigma2);
-        const double alpha = sigma * LQ[j * N + j];
-        Reflector rf = make_reflector(alpha, sigma2);
-        RY[j][j] = rf.beta;
-        // left block columns c > j
+        return make_reflector(sigma * LQ[j * N + j], sigma2);
+      };
+      auto apply_left = [&](const Reflector& rf, int j, int c) {
+        double top = sigma * LQ[c * N + j];
+        double w = 0.0;
 #pragma unroll
-        for (int c = j + 1; c < N; ++c) {
-          double top = sigma * LQ[c * N + j];
-          double w = rf.v0 * top;
+        for (int i = 0; i < N; ++i) w = fma(BL[i][j], BL[i][c], w);
+        w = fma(rf.v0, top, w);
+        double f = w * rf.g;
+        RY[j][c] = fma(-f, rf.v0, top);
 #pragma unroll
-          for (int i = 0; i < N; ++i) w = fma(BL[i][j], BL[i][c], w);
-          double f = w * rf.g;
-          RY[j][c] = fma(-f, rf.v0, top);
+        for (int i = 0; i < N; ++i) BL[i][c] = fma(-f, BL[i][j], BL[i][c]);
+      };
+      auto apply_right = [&](const Reflector& rf, int j, int c) {
+        double w = 0.0;  // the v0 term multiplies the (still zero) top-right entry
 #pragma unroll
-          for (int i = 0; i < N; ++i) BL[i][c] = fma(-f, BL[i][j], BL[i][c]);
+        for (int i = 0; i < N; ++i) {
+          if (j == 0 && i > c) continue;  // still structurally zero
+          w = fma(BL[i][j], BR[i][c], w);
         }
+        double f = w * rf.g;
+        R12[j][c] = fma(-f, rf.v0, 0.0);
+#pragma unroll
+        for (int i = 0; i < N; ++i) BR[i][c] = fma(-f, BL[i][j], BR[i][c]);
+      };
+      Reflector rf_next = column_reflector(0);
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        const Reflector rf = rf_next;
+        RY[j][j] = rf.beta;
+        if (j + 1 < N) {
+          apply_left(rf, j, j + 1);
+          rf_next = column_reflector(j + 1);
+        }
+#pragma unroll
+        for (int c = j + 2; c < N; ++c) apply_left(rf, j, c);
         if (FIX) {
-          // right block columns: top entry starts at 0
 #pragma unroll
-          for (int c = 0; c < N; ++c) {
-            double w = rf.v0 * 0.0;
-#pragma unroll
-            for (int i = 0; i < N; ++i) {
-              if (j == 0 && i > c) continue;  // still structurally zero
-              w = fma(BL[i][j], BR[i][c], w);
-            }
-            double f = w * rf.g;
-            R12[j][c] = fma(-f, rf.v0, 0.0);
-#pragma unroll
-            for (int i = 0; i < N; ++i) BR[i][c] = fma(-f, BL[i][j], BR[i][c]);
-          }
+          for (int c = 0; c < N; ++c) apply_right(rf, j, c);
         }
       }
 #pragma unroll
       for (int i = 0; i < N; ++i)
 #pragma unroll
         for (int j = 0; j <= i; ++j) L_ext[i][j] = p[i] * RY[j][i];
+    }
+    // correction (noise-free observation, sqrt form)
+    double m_new[N][D], L_new[N][N];
+    double e_norm;
+    {
+      double hL[Q + 1];
+      double S = 0.0;
+#pragma unroll
+      for (int j = 0; j <= Q; ++j) {
+        double acc = 0.0;
+#pragma unroll
+        for (int i = j; i <= Q; ++i) acc = fma(h[i], L_ext[i][j], acc);
+        hL[j] = acc;
+        S = fma(acc, acc, S);
+      }
+      double invS = rcp(S);
+      double gain[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j <= ((i < Q) ? i : Q); ++j) acc = fma(L_ext[i][j], hL[j], acc);
+        gain[i] = acc * invS;
+      }
+      // Mc[j][i] = L_ext[i][j] - hL[j] gain[i]; rows j > Q are untouched rows of L_ext^T
+      double Mc[Q + 1][N];
+#pragma unroll
+      for (int j = 0; j <= Q; ++j)
+#pragma unroll
+        for (int i = 0; i < N; ++i) Mc[j][i] = fma(-hL[j], gain[i], (j <= i) ? L_ext[i][j] : 0.0);
+#pragma unroll
+      for (int c0 = 0; c0 < Q; ++c0) {
+        double sigma2 = 0.0;
+#pragma unroll
+        for (int i = c0 + 1; i <= Q; ++i) sigma2 = fma(Mc[i][c0], Mc[i][c0], sigma2);
+        Reflector rf = make_reflector(Mc[c0][c0], sigma2);
+#pragma unroll
+        for (int c = c0 + 1; c < N; ++c) {
+          double w = 0.0;
+#pragma unroll
+          for (int i = c0 + 1; i <= Q; ++i) w = fma(Mc[i][c0], Mc[i][c], w);
+          w = fma(rf.v0, Mc[c0][c], w);
+          double f = w * rf.g;
+          Mc[c0][c] = fma(-f, rf.v0, Mc[c0][c]);
+#pragma unroll
+          for (int i = c0 + 1; i <= Q; ++i) Mc[i][c] = fma(-f, Mc[i][c0], Mc[i][c]);
+        }
+        Mc[c0][c0] = rf.beta;
+      }
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) L_new[i][j] = (j <= Q) ? Mc[j][i] : L_ext[i][j];
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int c = 0; c < D; ++c) m_new[i][c] = fma(-gain[i], z[c], m_ext[i][c]);
+      double acc = 0.0;
+      if (GROUP == 1) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          double ratio = err * rcp(fma(rtol, fabs(m_new[0][c]), atol));
+          acc = fma(ratio, ratio, acc);
+        }
+      } else {
+        double ratio = err * rcp(fma(rtol, fabs(m_new[0][0]), atol));
+        acc = group_sum<GROUP>(real ? fma(ratio, ratio, 0.0) : 0.0, gmask);
+      }
+      e_norm = dsqrt(acc) * inv_sqrt_d;
+    }
+    // PI controller
+    double fac;
+    {
+      double ie = rcp(e_norm);
+      double a1 = det_pow(ie, a.pow_i);
+      double a2 = det_pow(e_prev * ie, a.pow_p);
+      fac = (a.safety * a1) * a2;
+      fac = (fac < a.factor_max) ? fac : a.factor_max;
+      fac = (fac > a.factor_min) ? fac : a.factor_min;
+    }
+    // backward model of this prediction (fixed-point smoother): independent of the correction above
+    {
       if (FIX) {
         // phase 2: QR of the (now full) bottom-right block
 #pragma unroll
@@ -493,9 +591,10 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
           Reflector rf = make_reflector(BR[j][j], sigma2);
 #pragma unroll
           for (int c = j + 1; c < N; ++c) {
-            double w = rf.v0 * BR[j][c];
+            double w = 0.0;
 #pragma unroll
             for (int i = j + 1; i < N; ++i) w = fma(BR[i][j], BR[i][c], w);
+            w = fma(rf.v0, BR[j][c], w);
             double f = w * rf.g;
             BR[j][c] = fma(-f, rf.v0, BR[j][c]);
 #pragma unroll
@@ -583,11 +682,12 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
         Reflector rf = make_reflector(Mt[j][j], sigma2);
 #pragma unroll
         for (int c = j + 1; c < N; ++c) {
-          double w = rf.v0 * Mt[j][c];
+          double w = 0.0;
 #pragma unroll
           for (int i = j + 1; i < N; ++i) w = fma(Mt[i][j], Mt[i][c], w);
 #pragma unroll
           for (int i = 0; i <= j; ++i) w = fma(Mb[i][j], Mb[i][c], w);
+          w = fma(rf.v0, Mt[j][c], w);
           double f = w * rf.g;
           Mt[j][c] = fma(-f, rf.v0, Mt[j][c]);
 #pragma unroll
@@ -601,84 +701,6 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
       for (int i = 0; i < N; ++i)
 #pragma unroll
         for (int j = 0; j <= i; ++j) Lm[i][j] = Mt[j][i];
-    }
-    // correction (noise-free observation, sqrt form)
-    double m_new[N][D], L_new[N][N];
-    double e_norm;
-    {
-      double hL[Q + 1];
-      double S = 0.0;
-#pragma unroll
-      for (int j = 0; j <= Q; ++j) {
-        double acc = 0.0;
-#pragma unroll
-        for (int i = j; i <= Q; ++i) acc = fma(h[i], L_ext[i][j], acc);
-        hL[j] = acc;
-        S = fma(acc, acc, S);
-      }
-      double invS = rcp(S);
-      double gain[N];
-#pragma unroll
-      for (int i = 0; i < N; ++i) {
-        double acc = 0.0;
-#pragma unroll
-        for (int j = 0; j <= ((i < Q) ? i : Q); ++j) acc = fma(L_ext[i][j], hL[j], acc);
-        gain[i] = acc * invS;
-      }
-      // Mc[j][i] = L_ext[i][j] - hL[j] gain[i]; rows j > Q are untouched rows of L_ext^T
-      double Mc[Q + 1][N];
-#pragma unroll
-      for (int j = 0; j <= Q; ++j)
-#pragma unroll
-        for (int i = 0; i < N; ++i) Mc[j][i] = fma(-hL[j], gain[i], (j <= i) ? L_ext[i][j] : 0.0);
-#pragma unroll
-      for (int c0 = 0; c0 < Q; ++c0) {
-        double sigma2 = 0.0;
-#pragma unroll
-        for (int i = c0 + 1; i <= Q; ++i) sigma2 = fma(Mc[i][c0], Mc[i][c0], sigma2);
-        Reflector rf = make_reflector(Mc[c0][c0], sigma2);
-#pragma unroll
-        for (int c = c0 + 1; c < N; ++c) {
-          double w = rf.v0 * Mc[c0][c];
-#pragma unroll
-          for (int i = c0 + 1; i <= Q; ++i) w = fma(Mc[i][c0], Mc[i][c], w);
-          double f = w * rf.g;
-          Mc[c0][c] = fma(-f, rf.v0, Mc[c0][c]);
-#pragma unroll
-          for (int i = c0 + 1; i <= Q; ++i) Mc[i][c] = fma(-f, Mc[i][c0], Mc[i][c]);
-        }
-        Mc[c0][c0] = rf.beta;
-      }
-#pragma unroll
-      for (int i = 0; i < N; ++i)
-#pragma unroll
-        for (int j = 0; j <= i; ++j) L_new[i][j] = (j <= Q) ? Mc[j][i] : L_ext[i][j];
-#pragma unroll
-      for (int i = 0; i < N; ++i)
-#pragma unroll
-        for (int c = 0; c < D; ++c) m_new[i][c] = fma(-gain[i], z[c], m_ext[i][c]);
-      double acc = 0.0;
-      if (GROUP == 1) {
-#pragma unroll
-        for (int c = 0; c < D; ++c) {
-          double ratio = err * rcp(fma(rtol, fabs(m_new[0][c]), atol));
-          acc = fma(ratio, ratio, acc);
-        }
-      } else {
-        double ratio = err * rcp(fma(rtol, fabs(m_new[0][0]), atol));
-        acc = group_sum<GROUP>(real ? fma(ratio, ratio, 0.0) : 0.0, gmask);
-      }
-      e_norm = dsqrt(acc) * inv_sqrt_d;
-    }
-    // PI controller
-    double fac;
-    {
-      double ie = rcp(e_norm);
-      double a1 = det_pow(ie, a.pow_i);
-      double a2 = det_pow(e_prev * ie, a.pow_p);
-      fac = (a.safety * a1) * a2;
-      fac = (fac < a.factor_max) ? fac : a.factor_max;
-      fac = (fac > a.factor_min) ? fac : a.factor_min;
     }
     // ==================== per-lane bookkeeping (cheap, may diverge) =====================
     // helpers -------------------------------------------------------------------------
@@ -729,6 +751,11 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
         for (int j = 0; j <= i; ++j) dst[(long long)(N * D + Lay::tri(i, j)) * VB] = LL[i][j];
       }
     };
+    auto store_state = [&](double* dst) {  // committed hidden state (shared memory) -> workspace
+      if (!real) return;
+#pragma unroll
+      for (int e = 0; e < Lay::MARG; ++e) dst[(long long)e * VB] = s_state[e * THREADS + tid];
+    };
     auto record = [&](double tt, const double (&mm)[N][D], const double (&LL)[N][N]) {
       if (GROUP == 1 && (a.flags & FLAG_RECORD) && n_acc < a.traj_cap) {
         a.traj_t[n_acc * VB + vb] = tt;
@@ -748,11 +775,11 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
           }
           if (k_next == a.K - 1) {
             store_identity_cond(a.cond + vb);
-            store_marg(a.cond + (long long)Lay::BW * VB + vb, m, L);
+            store_state(a.cond + (long long)Lay::BW * VB + vb);
           }
           bw_reset();
         } else {
-          store_marg(slot, m, L);
+          store_state(slot);
         }
         if (sub == 0) a.n_accepted[b * a.K + k_next] = n_acc;
         k_next += 1;
@@ -763,12 +790,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
       t = SPEND(0);
       sigma_state = SPEND(1);
 #pragma unroll
-      for (int i = 0; i < N; ++i) {
-#pragma unroll
-        for (int c = 0; c < D; ++c) m[i][c] = SPEND(2 + i * D + c);
-#pragma unroll
-        for (int j = 0; j <= i; ++j) L[i][j] = SPEND(2 + N * D + Lay::tri(i, j));
-      }
+      for (int e = 0; e < Lay::MARG; ++e) s_state[e * THREADS + tid] = SPEND(2 + e);
     };
     // after a checkpoint was emitted while the accepted state waits in s_pend
     auto after_checkpoint = [&](bool& fin) {
@@ -816,9 +838,9 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
 #pragma unroll
             for (int i = 0; i < N; ++i) {
 #pragma unroll
-              for (int c = 0; c < D; ++c) m[i][c] = m_new[i][c];
+              for (int c = 0; c < D; ++c) SM(i, c) = m_new[i][c];
 #pragma unroll
-              for (int j = 0; j <= i; ++j) L[i][j] = L_new[i][j];
+              for (int j = 0; j <= i; ++j) SL(i, j) = L_new[i][j];
             }
             if (FIX) bw_commit();
             record(t1, m_new, L_new);
@@ -848,9 +870,9 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
 #pragma unroll
       for (int i = 0; i < N; ++i) {
 #pragma unroll
-        for (int c = 0; c < D; ++c) m[i][c] = m_ext[i][c];
+        for (int c = 0; c < D; ++c) SM(i, c) = m_ext[i][c];
 #pragma unroll
-        for (int j = 0; j <= i; ++j) L[i][j] = L_ext[i][j];
+        for (int j = 0; j <= i; ++j) SL(i, j) = L_ext[i][j];
       }
       if (sub == 0) a.n_accepted[b * a.K + k_next] = n_acc;
       if (FIX) {
@@ -893,6 +915,8 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
   }
 #undef SBW
 #undef SPEND
+#undef SM
+#undef SL
   (void)sigma_state;
 }
 

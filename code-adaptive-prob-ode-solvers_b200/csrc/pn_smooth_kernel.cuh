@@ -68,11 +68,12 @@ PN_DEV void marginalise_from_global(double (&m)[N][D], double (&L)[N][N], const 
     Reflector rf = make_reflector(Mt[j][j], sigma2);
 #pragma unroll
     for (int cc = j + 1; cc < N; ++cc) {
-      double w = rf.v0 * Mt[j][cc];
+      double w = 0.0;
 #pragma unroll
       for (int i = j + 1; i < N; ++i) w = fma(Mt[i][j], Mt[i][cc], w);
 #pragma unroll
       for (int i = 0; i <= j; ++i) w = fma(Mb[i][j], Mb[i][cc], w);
+      w = fma(rf.v0, Mt[j][cc], w);
       double f = w * rf.g;
       Mt[j][cc] = fma(-f, rf.v0, Mt[j][cc]);
 #pragma unroll

@@ -37,8 +37,11 @@ void pn_qr_r(double *M, int rows, int cols) {
     double beta = (alpha >= 0.0) ? -norm : norm;
     double g = 1.0 / (norm * (fabs(alpha) + norm)); /* = 2 / (v^T v) */
     for (int c = j + 1; c < cols; ++c) {
-      double w = v0 * M[j * cols + c];
+      /* w = v^T M[:, c]: the sub-diagonal part first (it does not depend on the reflector's norm,
+       * so a GPU can overlap it with the sqrt / reciprocal chain), the v0 term last */
+      double w = 0.0;
       for (int i = j + 1; i < rows; ++i) w = fma(M[i * cols + j], M[i * cols + c], w);
+      w = fma(v0, M[j * cols + c], w);
       double f = w * g;
       M[j * cols + c] = fma(-f, v0, M[j * cols + c]);
       for (int i = j + 1; i < rows; ++i) M[i * cols + c] = fma(-f, M[i * cols + j], M[i * cols + c]);
