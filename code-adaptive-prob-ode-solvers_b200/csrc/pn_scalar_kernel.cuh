@@ -418,9 +418,6 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
     double L_ext[N][N];         // lower
     double Gn[N][N], gn[N][D];  // new conditional (un-preconditioned); Lam_n lower
     double Ln[N][N];
-    double RY[N][N];   // upper
-    double R12[N][N];  // full (fixed-point)
-    double BR[N][N];   // bottom-right block, starts as L_p^T (upper), fills in (fixed-point)
     {
       double L_p[N][N];  // lower
 #pragma unroll
@@ -440,147 +437,57 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
           BL[j][i] = acc;
         }
       // top-left block rows: TL[j][c] = sigma * LQ[c][j] (c >= j), materialised when row j is used
+      double RY[N][N];   // upper
+      double R12[N][N];  // full (fixed-point)
+      double BR[N][N];   // bottom-right block, starts as L_p^T (upper), fills in (fixed-point)
       if (FIX) {
 #pragma unroll
         for (int i = 0; i < N; ++i)
 #pragma unroll
           for (int c = 0; c < N; ++c) BR[i][c] = (i <= c) ? L_p[c][i] : 0.0;
       }
-      // Phase 1 with look-ahead: reflector j+1 only needs left column j+1, so that column is updated
-      // first and the next reflector's serial chain (norm -> sqrt -> reciprocal) is issued BEFORE the
-      // bulk of reflector j's trailing updates, which ptxas then overlaps with it.  Same arithmetic
-      // per value as the plain column-by-column loop.
-      auto column_reflector = [&](int j) {
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
         double sigma2 = 0.0;
 #pragma unroll
         for (int i = 0; i < N; ++i) sigma2 = fma(BL[i][j], BL[i][j], sigma2);
-        return make_reflector(sigma * LQ[j * N + j], sigma2);
-      };
-      auto apply_left = [&](const Reflector& rf, int j, int c) {
-        double top = sigma * LQ[c * N + j];
-        double w = 0.0;
-#pragma unroll
-        for (int i = 0; i < N; ++i) w = fma(BL[i][j], BL[i][c], w);
-        w = fma(rf.v0, top, w);
-        double f = w * rf.g;
-        RY[j][c] = fma(-f, rf.v0, top);
-#pragma unroll
-        for (int i = 0; i < N; ++i) BL[i][c] = fma(-f, BL[i][j], BL[i][c]);
-      };
-      auto apply_right = [&](const Reflector& rf, int j, int c) {
-        double w = 0.0;  // the v0 term multiplies the (still zero) top-right entry
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-          if (j == 0 && i > c) continue;  // still structurally zero
-          w = fma(BL[i][j], BR[i][c], w);
-        }
-        double f = w * rf.g;
-        R12[j][c] = fma(-f, rf.v0, 0.0);
-#pragma unroll
-        for (int i = 0; i < N; ++i) BR[i][c] = fma(-f, BL[i][j], BR[i][c]);
-      };
-      Reflector rf_next = column_reflector(0);
-#pragma unroll
-      for (int j = 0; j < N; ++j) {
-        const Reflector rf = rf_next;
+        const double alpha = sigma * LQ[j * N + j];
+        Reflector rf = make_reflector(alpha, sigma2);
         RY[j][j] = rf.beta;
-        if (j + 1 < N) {
-          apply_left(rf, j, j + 1);
-          rf_next = column_reflector(j + 1);
+        // left block columns c > j
+#pragma unroll
+        for (int c = j + 1; c < N; ++c) {
+          double top = sigma * LQ[c * N + j];
+          double w = 0.0;
+#pragma unroll
+          for (int i = 0; i < N; ++i) w = fma(BL[i][j], BL[i][c], w);
+          w = fma(rf.v0, top, w);
+          double f = w * rf.g;
+          RY[j][c] = fma(-f, rf.v0, top);
+#pragma unroll
+          for (int i = 0; i < N; ++i) BL[i][c] = fma(-f, BL[i][j], BL[i][c]);
         }
-#pragma unroll
-        for (int c = j + 2; c < N; ++c) apply_left(rf, j, c);
         if (FIX) {
+          // right block columns: top entry starts at 0
 #pragma unroll
-          for (int c = 0; c < N; ++c) apply_right(rf, j, c);
+          for (int c = 0; c < N; ++c) {
+            double w = 0.0;  // the v0 term multiplies the (still zero) top-right entry
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+              if (j == 0 && i > c) continue;  // still structurally zero
+              w = fma(BL[i][j], BR[i][c], w);
+            }
+            double f = w * rf.g;
+            R12[j][c] = fma(-f, rf.v0, 0.0);
+#pragma unroll
+            for (int i = 0; i < N; ++i) BR[i][c] = fma(-f, BL[i][j], BR[i][c]);
+          }
         }
       }
 #pragma unroll
       for (int i = 0; i < N; ++i)
 #pragma unroll
         for (int j = 0; j <= i; ++j) L_ext[i][j] = p[i] * RY[j][i];
-    }
-    // correction (noise-free observation, sqrt form)
-    double m_new[N][D], L_new[N][N];
-    double e_norm;
-    {
-      double hL[Q + 1];
-      double S = 0.0;
-#pragma unroll
-      for (int j = 0; j <= Q; ++j) {
-        double acc = 0.0;
-#pragma unroll
-        for (int i = j; i <= Q; ++i) acc = fma(h[i], L_ext[i][j], acc);
-        hL[j] = acc;
-        S = fma(acc, acc, S);
-      }
-      double invS = rcp(S);
-      double gain[N];
-#pragma unroll
-      for (int i = 0; i < N; ++i) {
-        double acc = 0.0;
-#pragma unroll
-        for (int j = 0; j <= ((i < Q) ? i : Q); ++j) acc = fma(L_ext[i][j], hL[j], acc);
-        gain[i] = acc * invS;
-      }
-      // Mc[j][i] = L_ext[i][j] - hL[j] gain[i]; rows j > Q are untouched rows of L_ext^T
-      double Mc[Q + 1][N];
-#pragma unroll
-      for (int j = 0; j <= Q; ++j)
-#pragma unroll
-        for (int i = 0; i < N; ++i) Mc[j][i] = fma(-hL[j], gain[i], (j <= i) ? L_ext[i][j] : 0.0);
-#pragma unroll
-      for (int c0 = 0; c0 < Q; ++c0) {
-        double sigma2 = 0.0;
-#pragma unroll
-        for (int i = c0 + 1; i <= Q; ++i) sigma2 = fma(Mc[i][c0], Mc[i][c0], sigma2);
-        Reflector rf = make_reflector(Mc[c0][c0], sigma2);
-#pragma unroll
-        for (int c = c0 + 1; c < N; ++c) {
-          double w = 0.0;
-#pragma unroll
-          for (int i = c0 + 1; i <= Q; ++i) w = fma(Mc[i][c0], Mc[i][c], w);
-          w = fma(rf.v0, Mc[c0][c], w);
-          double f = w * rf.g;
-          Mc[c0][c] = fma(-f, rf.v0, Mc[c0][c]);
-#pragma unroll
-          for (int i = c0 + 1; i <= Q; ++i) Mc[i][c] = fma(-f, Mc[i][c0], Mc[i][c]);
-        }
-        Mc[c0][c0] = rf.beta;
-      }
-#pragma unroll
-      for (int i = 0; i < N; ++i)
-#pragma unroll
-        for (int j = 0; j <= i; ++j) L_new[i][j] = (j <= Q) ? Mc[j][i] : L_ext[i][j];
-#pragma unroll
-      for (int i = 0; i < N; ++i)
-#pragma unroll
-        for (int c = 0; c < D; ++c) m_new[i][c] = fma(-gain[i], z[c], m_ext[i][c]);
-      double acc = 0.0;
-      if (GROUP == 1) {
-#pragma unroll
-        for (int c = 0; c < D; ++c) {
-          double ratio = err * rcp(fma(rtol, fabs(m_new[0][c]), atol));
-          acc = fma(ratio, ratio, acc);
-        }
-      } else {
-        double ratio = err * rcp(fma(rtol, fabs(m_new[0][0]), atol));
-        acc = group_sum<GROUP>(real ? fma(ratio, ratio, 0.0) : 0.0, gmask);
-      }
-      e_norm = dsqrt(acc) * inv_sqrt_d;
-    }
-    // PI controller
-    double fac;
-    {
-      double ie = rcp(e_norm);
-      double a1 = det_pow(ie, a.pow_i);
-      double a2 = det_pow(e_prev * ie, a.pow_p);
-      fac = (a.safety * a1) * a2;
-      fac = (fac < a.factor_max) ? fac : a.factor_max;
-      fac = (fac > a.factor_min) ? fac : a.factor_min;
-    }
-    // backward model of this prediction (fixed-point smoother): independent of the correction above
-    {
       if (FIX) {
         // phase 2: QR of the (now full) bottom-right block
 #pragma unroll
@@ -701,6 +608,85 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
       for (int i = 0; i < N; ++i)
 #pragma unroll
         for (int j = 0; j <= i; ++j) Lm[i][j] = Mt[j][i];
+    }
+    // correction (noise-free observation, sqrt form)
+    double m_new[N][D], L_new[N][N];
+    double e_norm;
+    {
+      double hL[Q + 1];
+      double S = 0.0;
+#pragma unroll
+      for (int j = 0; j <= Q; ++j) {
+        double acc = 0.0;
+#pragma unroll
+        for (int i = j; i <= Q; ++i) acc = fma(h[i], L_ext[i][j], acc);
+        hL[j] = acc;
+        S = fma(acc, acc, S);
+      }
+      double invS = rcp(S);
+      double gain[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j <= ((i < Q) ? i : Q); ++j) acc = fma(L_ext[i][j], hL[j], acc);
+        gain[i] = acc * invS;
+      }
+      // Mc[j][i] = L_ext[i][j] - hL[j] gain[i]; rows j > Q are untouched rows of L_ext^T
+      double Mc[Q + 1][N];
+#pragma unroll
+      for (int j = 0; j <= Q; ++j)
+#pragma unroll
+        for (int i = 0; i < N; ++i) Mc[j][i] = fma(-hL[j], gain[i], (j <= i) ? L_ext[i][j] : 0.0);
+#pragma unroll
+      for (int c0 = 0; c0 < Q; ++c0) {
+        double sigma2 = 0.0;
+#pragma unroll
+        for (int i = c0 + 1; i <= Q; ++i) sigma2 = fma(Mc[i][c0], Mc[i][c0], sigma2);
+        Reflector rf = make_reflector(Mc[c0][c0], sigma2);
+#pragma unroll
+        for (int c = c0 + 1; c < N; ++c) {
+          double w = 0.0;
+#pragma unroll
+          for (int i = c0 + 1; i <= Q; ++i) w = fma(Mc[i][c0], Mc[i][c], w);
+          w = fma(rf.v0, Mc[c0][c], w);
+          double f = w * rf.g;
+          Mc[c0][c] = fma(-f, rf.v0, Mc[c0][c]);
+#pragma unroll
+          for (int i = c0 + 1; i <= Q; ++i) Mc[i][c] = fma(-f, Mc[i][c0], Mc[i][c]);
+        }
+        Mc[c0][c0] = rf.beta;
+      }
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) L_new[i][j] = (j <= Q) ? Mc[j][i] : L_ext[i][j];
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int c = 0; c < D; ++c) m_new[i][c] = fma(-gain[i], z[c], m_ext[i][c]);
+      double acc = 0.0;
+      if (GROUP == 1) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          double ratio = err * rcp(fma(rtol, fabs(m_new[0][c]), atol));
+          acc = fma(ratio, ratio, acc);
+        }
+      } else {
+        double ratio = err * rcp(fma(rtol, fabs(m_new[0][0]), atol));
+        acc = group_sum<GROUP>(real ? fma(ratio, ratio, 0.0) : 0.0, gmask);
+      }
+      e_norm = dsqrt(acc) * inv_sqrt_d;
+    }
+    // PI controller
+    double fac;
+    {
+      double ie = rcp(e_norm);
+      double a1 = det_pow(ie, a.pow_i);
+      double a2 = det_pow(e_prev * ie, a.pow_p);
+      fac = (a.safety * a1) * a2;
+      fac = (fac < a.factor_max) ? fac : a.factor_max;
+      fac = (fac > a.factor_min) ? fac : a.factor_min;
     }
     // ==================== per-lane bookkeeping (cheap, may diverge) =====================
     // helpers -------------------------------------------------------------------------
