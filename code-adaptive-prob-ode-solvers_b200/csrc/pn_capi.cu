@@ -62,6 +62,7 @@ static bool g_ev_ready = false, g_ev_recorded = false;
 struct Geometry {
   int dev;
   const KernelEntry* k;
+  size_t smem;
   int num_sms, ctas_per_sm;
 };
 static std::vector<Geometry> g_geom;
@@ -73,6 +74,7 @@ struct Plan {
   size_t smem = 0;
   size_t ws_ticket = 256;  // bytes reserved for the work-queue ticket
   size_t ws_cond = 0;      // bytes of conditionals
+  size_t ws_wide = 0;      // wide kernels: per-member mean arrays
 };
 
 static int resolve(const pn_b200_desc* d, const KernelEntry** out) {
@@ -101,6 +103,10 @@ static int resolve(const pn_b200_desc* d, const KernelEntry** out) {
   // warp-per-IVP dense family: dense factorisation with d > 1, EKF0 or EKF1
   if (!k && d->factorisation == PN_B200_DENSE && d->d > 1)
     k = find_kernel(FAMILY_DENSE, d->problem, d->nu, d->strategy, d->d);
+  // CTA-per-IVP wide family: isotropic EKF0 with a runtime dimension (Brusselator beyond the fixed sizes)
+  if (!k && d->correction == PN_B200_TS0 && d->factorisation == PN_B200_ISOTROPIC && d->d >= 4 && d->d <= 4096 &&
+      (d->d % 2) == 0)
+    k = find_kernel(FAMILY_WIDE, d->problem, d->nu, d->strategy, 0);
   if (k && k->group > 1 && (d->flags & PN_B200_FLAG_RECORD))
     return fail(PN_B200_ERR_UNSUPPORTED, "trajectory recording is implemented for the thread-per-IVP kernels");
   if (!k) {
@@ -122,7 +128,13 @@ static int make_plan(const pn_b200_desc* d, Plan* p, bool need_device) {
   p->smem = (p->k->family == FAMILY_DENSE)
                 ? (size_t)p->k->smem_doubles * (p->k->threads / 32) * sizeof(double)  // per warp
                 : (size_t)p->k->smem_doubles * p->k->threads * sizeof(double);        // per thread
+  if (p->k->family == FAMILY_WIDE) p->smem += ((size_t)2 * d->d + p->k->threads / 32 + 2) * sizeof(double);
   p->ws_cond = (size_t)d->num_save_at * p->k->slot_doubles * (size_t)d->batch * p->k->dv * sizeof(double);
+  if (p->k->family == FAMILY_WIDE) {
+    const size_t nd = (size_t)(d->nu + 1) * d->d;
+    p->ws_cond = (size_t)d->batch * ((size_t)d->num_save_at * (p->k->slot_doubles + 2 * nd)) * sizeof(double);
+    p->ws_wide = (size_t)d->batch * 3 * nd * sizeof(double);
+  }
   if (!need_device) return PN_B200_SUCCESS;
   int dev = 0;
   cudaError_t ce = cudaGetDevice(&dev);
@@ -131,7 +143,7 @@ static int make_plan(const pn_b200_desc* d, Plan* p, bool need_device) {
   {
     std::lock_guard<std::mutex> lock(g_geom_mutex);
     for (const auto& g : g_geom)
-      if (g.dev == dev && g.k == p->k) {
+      if (g.dev == dev && g.k == p->k && g.smem == p->smem) {
         p->num_sms = g.num_sms;
         p->ctas_per_sm = g.ctas_per_sm;
       }
@@ -147,10 +159,10 @@ static int make_plan(const pn_b200_desc* d, Plan* p, bool need_device) {
     if (occ < 1) return fail(PN_B200_ERR_CUDA, "kernel does not fit on an SM");
     p->ctas_per_sm = occ;
     std::lock_guard<std::mutex> lock(g_geom_mutex);
-    g_geom.push_back({dev, p->k, p->num_sms, occ});
+    g_geom.push_back({dev, p->k, p->smem, p->num_sms, occ});
   }
   const int occ = p->ctas_per_sm;
-  const long long per_cta = p->k->threads / p->k->group;  // IVPs a CTA holds at a time
+  const long long per_cta = (p->k->family == FAMILY_WIDE) ? 1 : p->k->threads / p->k->group;  // IVPs per CTA
   long long want = (d->batch + per_cta - 1) / per_cta;
   long long cap = (long long)occ * p->num_sms;
   p->grid = (int)(want < cap ? want : cap);
@@ -202,7 +214,7 @@ int pn_b200_supported(const pn_b200_desc* desc) {
 size_t pn_b200_workspace_bytes(const pn_b200_desc* desc) {
   Plan p;
   if (make_plan(desc, &p, false)) return 0;
-  return p.ws_ticket + p.ws_cond;
+  return p.ws_ticket + p.ws_cond + p.ws_wide;
 }
 
 int pn_b200_get_kernel_info(const pn_b200_desc* desc, pn_b200_kernel_info* info) {
@@ -238,7 +250,7 @@ int pn_b200_solve_save_at(const pn_b200_desc* desc, const double* u0, const doub
   if (desc->num_params > 0 && !params) return fail(PN_B200_ERR_ARGUMENT, "params is null but num_params > 0");
   if ((desc->flags & PN_B200_FLAG_RECORD) && (!traj_t || !traj_u || !traj_std || !traj_len || desc->traj_capacity < 2))
     return fail(PN_B200_ERR_ARGUMENT, "trajectory recording needs traj buffers and traj_capacity >= 2");
-  if (!workspace || workspace_bytes < p.ws_ticket + p.ws_cond) return fail(PN_B200_ERR_WORKSPACE, "workspace too small");
+  if (!workspace || workspace_bytes < p.ws_ticket + p.ws_cond + p.ws_wide) return fail(PN_B200_ERR_WORKSPACE, "workspace too small");
   cudaStream_t stream = (cudaStream_t)cuda_stream;
 
   SolveArgs a;
@@ -266,6 +278,8 @@ int pn_b200_solve_save_at(const pn_b200_desc* desc, const double* u0, const doub
   a.sigma0 = output_scale0;
   a.ticket = (unsigned long long*)workspace;
   a.cond = (double*)((char*)workspace + p.ws_ticket);
+  a.wide_d = (p.k->family == FAMILY_WIDE) ? desc->d : 0;
+  a.wide_mean = (double*)((char*)workspace + p.ws_ticket + p.ws_cond);
   a.n_accepted = (long long*)n_accepted;
   a.n_rejected = (long long*)n_rejected;
   a.status = status;
@@ -296,6 +310,8 @@ int pn_b200_solve_save_at(const pn_b200_desc* desc, const double* u0, const doub
   s.K = desc->num_save_at;
   s.dv = p.k->dv;
   s.chol_per_dim = (p.k->family == FAMILY_GROUP_BDIAG) ? 1 : 0;
+  s.wide_d = a.wide_d;
+  s.wide_mean = a.wide_mean;
   s.cond = a.cond;
   s.status = status;
   s.u = u;

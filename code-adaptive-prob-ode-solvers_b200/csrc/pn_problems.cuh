@@ -315,6 +315,21 @@ struct Brusselator {
   }
 };
 
+// Brusselator with a RUNTIME grid size (CTA-per-IVP "wide" kernel): the vector field and the Taylor
+// initialisation are written out inside the kernel (they need the CTA's shared staging buffers);
+// this tag only carries the compile-time facts.  D is a dummy register column.
+struct BrusselatorWide {
+  static constexpr int D = 1, Q = 1, P = 1, ID = 4;
+  static constexpr bool HAS_JAC = false;
+  PN_DEV static void vf(const double*, const double*, double* f) { f[0] = 0.0; }
+  PN_DEV static void jac(const double*, const double*, double*) {}
+  template <int N>
+  PN_DEV static void vf_jet(const double*, const double*, double* F) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) F[k] = 0.0;
+  }
+};
+
 // taylor.odejet_padded_scan replacement: tc[k][l] = u_l^{(k)}(t0), k = 0..NU.
 template <class Prob, int NU>
 PN_DEV void taylor_init(const double* u0 /*[Q*D]*/, const double* par, double (&tc)[NU + 1][Prob::D]) {

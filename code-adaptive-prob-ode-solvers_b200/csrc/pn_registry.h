@@ -12,7 +12,8 @@ enum : int {
   FAMILY_SCALAR = 0,      // thread per IVP, one n x n factor shared by all mean columns
   FAMILY_GROUP_ISO = 1,   // lane per dimension, identical factors (isotropic)
   FAMILY_GROUP_BDIAG = 2, // lane per dimension, per-dimension factors (blockdiag)
-  FAMILY_DENSE = 3        // warp per IVP, D x D factors in shared memory (dense, d > 1)
+  FAMILY_DENSE = 3,       // warp per IVP, D x D factors in shared memory (dense, d > 1)
+  FAMILY_WIDE = 4         // CTA per IVP, isotropic, runtime dimension (Brusselator d = 2N up to 4096)
 };
 
 struct KernelEntry {
@@ -109,6 +110,44 @@ struct DenseInstance {
   }
 };
 
+// isotropic problems with a large runtime dimension: CTA per IVP
+template <class Prob, int NU, int STRAT, int THREADS>
+struct WideInstance {
+  using Lay = Layout<NU + 1, 1>;
+  static cudaError_t launch_solve(const SolveArgs& a, int grid, size_t smem, cudaStream_t s) {
+    pn_scalar_kernel<Prob, NU, STRAT, 1, 0, THREADS, 1><<<grid, THREADS, smem, s>>>(a);
+    return cudaGetLastError();
+  }
+  static cudaError_t launch_smooth(const SmoothArgs& a, cudaStream_t s) {
+    WideSmoothArgs w;
+    w.B = a.B; w.K = a.K; w.d = a.wide_d; w.cond = a.cond; w.mean = a.wide_mean; w.status = a.status;
+    w.u = a.u; w.u_std = a.u_std; w.marg_mean = a.marg_mean; w.marg_chol = a.marg_chol;
+    pn_wide_smooth_kernel<NU + 1, STRAT, THREADS><<<(int)a.B, THREADS, 0, s>>>(w);
+    return cudaGetLastError();
+  }
+  static KernelEntry entry() {
+    KernelEntry e;
+    e.family = FAMILY_WIDE;
+    e.group = THREADS;
+    e.dv = 1;
+    e.problem = Prob::ID;
+    e.nu = NU;
+    e.strategy = STRAT;
+    e.N = NU + 1;
+    e.D = 0;  // runtime dimension
+    e.Q = Prob::Q;
+    e.P = Prob::P;
+    e.slot_doubles = Lay::BW + Lay::NT;  // factor part of a slot; + 2 n d per slot and 3 n d per member at run time
+    e.smem_doubles = ((STRAT == 1) ? Lay::BW : 0) + Lay::PEND + Lay::MARG;  // per thread; + 2 d + warps per CTA
+    e.threads = THREADS;
+    e.has_jac = false;
+    e.solve_func = (const void*)&pn_scalar_kernel<Prob, NU, STRAT, 1, 0, THREADS, 1>;
+    e.launch_solve = &launch_solve;
+    e.launch_smooth = &launch_smooth;
+    return e;
+  }
+};
+
 struct Registrar {
   explicit Registrar(const KernelEntry& e) { register_kernel(e); }
 };
@@ -119,6 +158,8 @@ struct Registrar {
   static ::pn::Registrar PN_CAT(pn_reg_, __COUNTER__)(::pn::ScalarInstance<::pn::Prob, NU, STRAT, 1, 0, 128>::entry())
 #define PN_REGISTER_DENSE(Prob, NU, STRAT, WARPS) \
   static ::pn::Registrar PN_CAT(pn_reg_, __COUNTER__)(::pn::DenseInstance<::pn::Prob, NU, STRAT, WARPS>::entry())
+#define PN_REGISTER_WIDE(Prob, NU, STRAT) \
+  static ::pn::Registrar PN_CAT(pn_reg_, __COUNTER__)(::pn::WideInstance<::pn::Prob, NU, STRAT, 128>::entry())
 // lane-per-dimension kernels: GROUP lanes per IVP, BDIAG = 1 blockdiag / 0 isotropic
 #define PN_REGISTER_GROUP(Prob, NU, STRAT, GROUP, BDIAG) \
   static ::pn::Registrar PN_CAT(pn_reg_, __COUNTER__)(::pn::ScalarInstance<::pn::Prob, NU, STRAT, GROUP, BDIAG, 128>::entry())

@@ -66,6 +66,10 @@ struct SolveArgs {
   double* traj_std;  // [cap][B]   (isotropic: one std for all dimensions)
   long long traj_cap;
   long long* traj_len;  // [B]
+  // wide (CTA-per-IVP) kernel only: runtime ODE dimension and the per-member mean arrays
+  // [B][3][n][d] (state mean, backward-conditional offset g, pending mean) in global memory
+  int wide_d;
+  double* wide_mean;
   // Prior constant: lower Cholesky factor of the flipped Hilbert matrix, row-major
   // n x n, computed by the host (pn_capi.cu).  Kernel parameters live in the constant bank, so
   // DFMA reads these entries as immediate constant operands.
@@ -180,7 +184,12 @@ struct GroupVf<Brusselator<NPTS>, GROUP> {
 // GROUP > 1: GROUP lanes per IVP, lane `sub` owns ODE dimension `sub` (one mean column) and a full
 //            n x n factor set: per-dimension factors for BDIAG (blockdiag factorisation), replicated
 //            identical factors for the isotropic factorisation.
-template <class Prob, int NU, int STRAT, int GROUP, int BDIAG, int THREADS>
+// WIDE = 1: one CTA per IVP for isotropic problems with a large runtime dimension d (Brusselator,
+//           d = 2N up to 2048).  Every thread carries the same n x n factor state and executes the
+//           same factor arithmetic as a thread-per-IVP lane; the n x d mean arrays live in global
+//           memory (L2 resident) and each thread owns the columns c = tid, tid + THREADS, ...;
+//           norms are reduced over the CTA.  Prob::D is a dummy (1) in this mode.
+template <class Prob, int NU, int STRAT, int GROUP, int BDIAG, int THREADS, int WIDE = 0>
 __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const __grid_constant__ SolveArgs a) {
   constexpr int N = NU + 1, DT = Prob::D, D = (GROUP > 1) ? 1 : DT, Q = Prob::Q, P = (Prob::P > 0 ? Prob::P : 1);
   constexpr int DV = (GROUP > 1) ? DT : 1;  // lanes ("virtual members") per IVP that own state
@@ -204,13 +213,39 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
   constexpr int OFF_G = 0, OFF_g = N * N, OFF_LAM = N * N + N * D;
 
   const double* LQ = a.lq;
-  const double inv_sqrt_d = rcp(dsqrt((double)DT));
+  const double inv_sqrt_d = rcp(dsqrt((double)(WIDE ? a.wide_d : DT)));
   const int lane = threadIdx.x & 31;
   const int sub = (GROUP > 1) ? (lane & (GROUP - 1)) : 0;   // dimension owned by this lane
   const int base = lane - sub;                               // first lane of the group
   const unsigned gmask = (GROUP >= 32) ? 0xffffffffu : (((1u << GROUP) - 1u) << base);
-  const bool real = sub < DT;                                // padding lanes carry no dimension
-  const long long VB = a.B * DV;                             // stride of the member-minor workspace
+  const bool real = WIDE ? false : (sub < DT);               // padding lanes carry no dimension; the wide
+                                                             // mode has its own workspace stores
+  const bool leader = WIDE ? (threadIdx.x == 0) : (sub == 0);  // writes the per-member counters
+  const long long VB = WIDE ? 1 : a.B * DV;                  // stride of the member-minor workspace
+  // ---- wide mode: dimensions, per-member arrays, shared staging buffers ---------------------
+  const int wd = WIDE ? a.wide_d : 0;                        // runtime ODE dimension
+  const int wN = wd / 2;                                     // Brusselator grid points
+  constexpr int WSLOT = Lay::BW + Lay::NT;                   // factor part of a wide slot: (G, -, Lam) + L1
+  const long long wslot = WIDE ? (long long)WSLOT + 2LL * N * wd : 0;  // + g [n][d] + m1 [n][d]
+  double* s_ubuf = smem + ((FIX ? Lay::BW : 0) + Lay::PEND + Lay::MARG) * THREADS;  // [d] predicted u
+  double* s_zbuf = s_ubuf + wd;                                                      // [d] residual z
+  double* s_red = s_zbuf + wd;                                                       // [THREADS/32]
+  double* Wm = nullptr;    // state mean [n][d]
+  double* Wg = nullptr;    // backward-conditional offset g [n][d]
+  double* Wp = nullptr;    // pending (accepted, uncommitted) mean [n][d]
+  double* wcond = nullptr; // this member's slots [K][wslot]
+  auto block_sum = [&](double v) -> double {
+    // fixed order: per-warp butterfly, then the warp sums added in warp order
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, off);
+    __syncthreads();
+    if ((tid & 31) == 0) s_red[tid >> 5] = v;
+    __syncthreads();
+    double r = s_red[0];
+#pragma unroll
+    for (int w = 1; w < THREADS / 32; ++w) r = r + s_red[w];
+    return r;
+  };
 
   // ---- per-lane persistent state --------------------------------------------------------
   bool have = false, exhausted = false;
@@ -229,21 +264,84 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
     // ---- fetch a member ----------------------------------------------------------------
     if (!have && !exhausted) {
       unsigned long long tk = 0;
-      if (sub == 0) tk = atomicAdd(a.ticket, 1ULL);
-      if (GROUP > 1) tk = __shfl_sync(gmask, tk, base);
+      if constexpr (WIDE) {
+        __shared__ unsigned long long s_ticket;
+        __syncthreads();
+        if (tid == 0) s_ticket = atomicAdd(a.ticket, 1ULL);
+        __syncthreads();
+        tk = s_ticket;
+      } else {
+        if (sub == 0) tk = atomicAdd(a.ticket, 1ULL);
+        if (GROUP > 1) tk = __shfl_sync(gmask, tk, base);
+      }
       if (tk < (unsigned long long)a.B) {
         b = (long long)tk;
-        vb = b * DV + ((GROUP > 1 && real) ? sub : 0);
+        vb = WIDE ? 0 : (b * DV + ((GROUP > 1 && real) ? sub : 0));
         have = true;
         double u0[Q * DT];
+        if constexpr (!WIDE) {
 #pragma unroll
-        for (int i = 0; i < Q * DT; ++i) u0[i] = a.u0[b * (Q * DT) + i];
+          for (int i = 0; i < Q * DT; ++i) u0[i] = a.u0[b * (Q * DT) + i];
+        }
 #pragma unroll
         for (int i = 0; i < P; ++i) par[i] = (i < a.num_params) ? a.params[b * a.num_params + i] : 0.0;
         atol = a.tol ? a.tol[2 * b] : a.atol;
         rtol = a.tol ? a.tol[2 * b + 1] : a.rtol;
         sigma0 = a.sigma0 ? a.sigma0[b] : 1.0;
-        {
+        if constexpr (WIDE) {
+          Wm = a.wide_mean + (size_t)b * 3 * N * wd;
+          Wg = Wm + (size_t)N * wd;
+          Wp = Wg + (size_t)N * wd;
+          wcond = a.cond + (size_t)b * a.K * wslot;
+          // Taylor-mode initialisation of the Brusselator, one grid point per thread and order
+          // (normalised coefficients C_k in Wm; the k-th coefficient of f only needs C_0..C_k)
+          const double cc = par[0] * (double)((wN + 1) * (wN + 1));
+          for (int c = tid; c < wd; c += THREADS) {
+            Wm[c] = a.u0[b * wd + c];
+            for (int i = 1; i < N; ++i) Wm[(size_t)i * wd + c] = 0.0;
+            for (int i = 0; i < N; ++i) Wg[(size_t)i * wd + c] = 0.0;
+          }
+          __syncthreads();
+          for (int k = 0; k < NU; ++k) {
+            for (int gi = tid; gi < wN; gi += THREADS) {
+              double uj[N], vj[N], u2[N];
+              for (int j = 0; j <= k; ++j) {
+                uj[j] = Wm[(size_t)j * wd + gi];
+                vj[j] = Wm[(size_t)j * wd + wN + gi];
+              }
+              for (int kk = 0; kk <= k; ++kk) {
+                double acc = uj[0] * uj[kk];
+                for (int j = 1; j <= kk; ++j) acc = fma(uj[j], uj[kk - j], acc);
+                u2[kk] = acc;
+              }
+              double uuv = u2[0] * vj[k];
+              for (int j = 1; j <= k; ++j) uuv = fma(u2[j], vj[k - j], uuv);
+              const double padu = (k == 0) ? 1.0 : 0.0, padv = (k == 0) ? 3.0 : 0.0;
+              const double ul = (gi == 0) ? padu : Wm[(size_t)k * wd + gi - 1];
+              const double ur = (gi == wN - 1) ? padu : Wm[(size_t)k * wd + gi + 1];
+              const double vl = (gi == 0) ? padv : Wm[(size_t)k * wd + wN + gi - 1];
+              const double vr = (gi == wN - 1) ? padv : Wm[(size_t)k * wd + wN + gi + 1];
+              const double lap_u = fma(-2.0, uj[k], ul + ur);
+              const double lap_v = fma(-2.0, vj[k], vl + vr);
+              const double fu = fma(cc, lap_u, fma(-4.0, uj[k], padu + uuv));
+              const double fv = fma(cc, lap_v, fma(3.0, uj[k], -uuv));
+              // row k+1 is not read by anybody during this sweep
+              Wm[(size_t)(k + 1) * wd + gi] = fu / (double)(k + 1);
+              Wm[(size_t)(k + 1) * wd + wN + gi] = fv / (double)(k + 1);
+            }
+            __syncthreads();
+          }
+          {
+            double fact = 1.0;
+            for (int k = 0; k <= NU; ++k) {
+              if (k > 0) fact *= (double)k;
+              for (int c = tid; c < wd; c += THREADS) Wm[(size_t)k * wd + c] = fact * Wm[(size_t)k * wd + c];
+            }
+          }
+          __syncthreads();
+#pragma unroll
+          for (int i = 0; i < N; ++i) SM(i, 0) = 0.0;  // dummy register column
+        } else {
           double tc[N][DT];
           taylor_init<Prob, NU>(u0, par, tc);
 #pragma unroll
@@ -276,14 +374,19 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
         mode = MODE_STEP;
         k_next = 1;
         n_acc = n_rej = n_att = 0;
-        if (sub == 0) a.n_accepted[b * a.K] = 0;
+        if (leader) a.n_accepted[b * a.K] = 0;
         if (GROUP == 1 && (a.flags & FLAG_RECORD)) {
           a.traj_t[b] = t;
 #pragma unroll
           for (int c = 0; c < D; ++c) a.traj_u[(long long)c * a.B + b] = SM(0, c);
           a.traj_std[b] = 0.0;
         }
-        if (!FIX && real) {
+        if constexpr (WIDE) {
+          if (!FIX) {  // filter: slot 0 holds the initial marginal (factor part zero)
+            for (int e = tid; e < WSLOT; e += THREADS) wcond[e] = 0.0;
+            for (int e = tid; e < N * wd; e += THREADS) wcond[WSLOT + (size_t)N * wd + e] = Wm[e];
+          }
+        } else if (!FIX && real) {
           // filter: slot 0 holds the initial marginal
 #pragma unroll
           for (int i = 0; i < N; ++i) {
@@ -389,6 +492,42 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
         for (int k = 0; k < Q; ++k) h[k] = -J[k];
       }
     }
+    // wide mode, pass 1: per owned column predict the mean, stage u = m_ext[0] for the stencil,
+    // form the residual z (kept in shared memory) and the CTA-wide sum of squares
+    double wide_zz = 0.0;
+    if constexpr (WIDE) {
+      for (int c = tid; c < wd; c += THREADS) {
+        double mp[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) mp[i] = pinv[i] * Wm[(size_t)i * wd + c];
+        double e0 = mp[0], e1 = mp[1];
+#pragma unroll
+        for (int j = 1; j < N; ++j) e0 = fma(Binom<N>::at(0, j), mp[j], e0);
+#pragma unroll
+        for (int j = 2; j < N; ++j) e1 = fma(Binom<N>::at(1, j), mp[j], e1);
+        s_ubuf[c] = p[0] * e0;
+        s_zbuf[c] = p[1] * e1;  // m_ext[q = 1][c] for now
+      }
+      __syncthreads();
+      const double cc = par[0] * (double)((wN + 1) * (wN + 1));
+      double acc = 0.0;
+      for (int c = tid; c < wd; c += THREADS) {
+        const bool isu = c < wN;
+        const int gi = isu ? c : c - wN;
+        const double me = s_ubuf[c];
+        const double pad = isu ? 1.0 : 3.0;
+        const double l = (gi == 0) ? pad : s_ubuf[c - 1];
+        const double r = (gi == wN - 1) ? pad : s_ubuf[c + 1];
+        const double ui = s_ubuf[gi], vi = s_ubuf[wN + gi];
+        const double uuv = (ui * ui) * vi;
+        const double lap = fma(-2.0, me, l + r);
+        const double f = isu ? fma(cc, lap, fma(-4.0, ui, 1.0 + uuv)) : fma(cc, lap, fma(3.0, ui, -uuv));
+        const double zc = s_zbuf[c] - f;
+        acc = fma(zc, zc, acc);
+        s_zbuf[c] = zc;  // own column only: no hazard
+      }
+      wide_zz = block_sum(acc);
+    }
     // local calibration + error estimate from the process noise
     double err, sigma;
     {
@@ -402,7 +541,9 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
       }
       double s = dsqrt(s2);
       double zz = 0.0;
-      if (GROUP == 1) {
+      if constexpr (WIDE) {
+        zz = wide_zz;
+      } else if (GROUP == 1) {
 #pragma unroll
         for (int c = 0; c < D; ++c) zz = fma(z[c], z[c], zz);
       } else {
@@ -418,6 +559,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
     double L_ext[N][N];         // lower
     double Gn[N][N], gn[N][D];  // new conditional (un-preconditioned); Lam_n lower
     double Ln[N][N];
+    double X[N][N];             // RY^{-1} R12 (fixed-point); G_p = X^T
     {
       double L_p[N][N];  // lower
 #pragma unroll
@@ -510,7 +652,6 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
           BR[j][j] = rf.beta;
         }
         // X = RY^{-1} R12 (back substitution); G_p = X^T
-        double X[N][N];
 #pragma unroll
         for (int i = N - 1; i >= 0; --i) {
           double inv = rcp(RY[i][i]);
@@ -611,6 +752,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
     }
     // correction (noise-free observation, sqrt form)
     double m_new[N][D], L_new[N][N];
+    double gain[N];
     double e_norm;
     {
       double hL[Q + 1];
@@ -624,7 +766,6 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
         S = fma(acc, acc, S);
       }
       double invS = rcp(S);
-      double gain[N];
 #pragma unroll
       for (int i = 0; i < N; ++i) {
         double acc = 0.0;
@@ -666,7 +807,16 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
 #pragma unroll
         for (int c = 0; c < D; ++c) m_new[i][c] = fma(-gain[i], z[c], m_ext[i][c]);
       double acc = 0.0;
-      if (GROUP == 1) {
+      if constexpr (WIDE) {
+        // pass 2: proposed u = m_new[0][c] = m_ext[0][c] - gain[0] z[c] per owned column
+        double part = 0.0;
+        for (int c = tid; c < wd; c += THREADS) {
+          const double u_new = fma(-gain[0], s_zbuf[c], s_ubuf[c]);
+          const double ratio = err * rcp(fma(rtol, fabs(u_new), atol));
+          part = fma(ratio, ratio, part);
+        }
+        acc = block_sum(part);
+      } else if (GROUP == 1) {
 #pragma unroll
         for (int c = 0; c < D; ++c) {
           double ratio = err * rcp(fma(rtol, fabs(m_new[0][c]), atol));
@@ -691,6 +841,103 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
     // ==================== per-lane bookkeeping (cheap, may diverge) =====================
     // helpers -------------------------------------------------------------------------
     auto ck_time = [&](long long k) { return a.save_at[k < a.K ? k : a.K - 1]; };
+    // wide mode, pass 3: everything the bookkeeping below does to the n x d mean arrays, in ONE
+    // sweep over the owned columns (reads the old state, writes the new one).
+    //   mw: what becomes the state mean   (0 keep, 1 m_new, 2 m_ext, 3 pending mean)
+    //   gw: what becomes the running g    (0 keep, 1 merged gm, 2 zero)
+    //   pw: pending mean <- m_new
+    //   eg / em: global destinations [n][d] for the merged g / a mean to emit (nullptr: none)
+    //   em_src: 2 m_ext, 3 pending mean
+    auto wide_pass3 = [&](int mw, int gw, bool pw, double* eg, double* em, int em_src) {
+      if constexpr (WIDE) {
+        for (int c = tid; c < wd; c += THREADS) {
+          double mo[N], mp[N], mep[N], mext[N];
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+            mo[i] = Wm[(size_t)i * wd + c];
+            mp[i] = pinv[i] * mo[i];
+          }
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+            double acc = mp[i];
+#pragma unroll
+            for (int j = i + 1; j < N; ++j) acc = fma(Binom<N>::at(i, j), mp[j], acc);
+            mep[i] = acc;
+            mext[i] = p[i] * acc;
+          }
+          const double zc = s_zbuf[c];
+          double gmc[N];
+          if (FIX && (gw == 1 || eg != nullptr)) {
+            double gnc[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+              double acc = mp[i];
+#pragma unroll
+              for (int k = 0; k < N; ++k) acc = fma(-X[k][i], mep[k], acc);
+              gnc[i] = p[i] * acc;
+            }
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+              double acc = Wg[(size_t)i * wd + c];
+#pragma unroll
+              for (int k = 0; k < N; ++k) acc = fma(SBW(OFF_G + i * N + k), gnc[k], acc);
+              gmc[i] = acc;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+            const double mn = fma(-gain[i], zc, mext[i]);
+            const double pend_old = (mw == 3 || em_src == 3) ? Wp[(size_t)i * wd + c] : 0.0;
+            if (pw) Wp[(size_t)i * wd + c] = mn;
+            if (mw == 1) Wm[(size_t)i * wd + c] = mn;
+            if (mw == 2) Wm[(size_t)i * wd + c] = mext[i];
+            if (mw == 3) Wm[(size_t)i * wd + c] = pend_old;
+            if (FIX && gw == 1) Wg[(size_t)i * wd + c] = gmc[i];
+            if (FIX && gw == 2) Wg[(size_t)i * wd + c] = 0.0;
+            if (FIX && eg != nullptr) eg[(size_t)i * wd + c] = gmc[i];
+            if (em != nullptr) em[(size_t)i * wd + c] = (em_src == 2) ? mext[i] : pend_old;
+          }
+        }
+        __syncthreads();
+      }
+    };
+    // wide slot layout: [G | (unused n) | Lam | L1 | g (n x d) | m1 (n x d)]; src 0: merged result of
+    // this step, 1: identity, 2: the committed running conditional (shared memory)
+    auto wide_store_factor = [&](double* dst, int src) {
+      if constexpr (WIDE) {
+        if (tid == 0) {
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+#pragma unroll
+            for (int j = 0; j < N; ++j)
+              dst[OFF_G + i * N + j] = (src == 1) ? ((i == j) ? 1.0 : 0.0) : ((src == 2) ? SBW(OFF_G + i * N + j) : Gm[i][j]);
+            dst[OFF_g + i] = 0.0;
+#pragma unroll
+            for (int j = 0; j <= i; ++j)
+              dst[OFF_LAM + Lay::tri(i, j)] = (src == 1) ? 0.0 : ((src == 2) ? SBW(OFF_LAM + Lay::tri(i, j)) : Lm[i][j]);
+          }
+        }
+      }
+    };
+    // L1 part of a wide slot; src 0: committed factor, 1: pending factor, 2: L_ext of this step
+    auto wide_store_L1 = [&](double* dst, int src) {
+      if constexpr (WIDE) {
+        if (tid == 0) {
+#pragma unroll
+          for (int i = 0; i < N; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j)
+              dst[Lay::BW + Lay::tri(i, j)] = (src == 0) ? SL(i, j) : ((src == 1) ? SPEND(2 + N * D + Lay::tri(i, j)) : L_ext[i][j]);
+        }
+      }
+    };
+    auto wide_copy = [&](double* dst, const double* src, bool zero_src) {  // [n][d] arrays
+      if constexpr (WIDE) {
+        for (int e = tid; e < N * wd; e += THREADS) dst[e] = zero_src ? 0.0 : src[e];
+        __syncthreads();
+      }
+    };
+
     auto store_cond = [&](double* dst /* element stride VB */) {
       if (!real) return;
 #pragma unroll
@@ -754,6 +1001,23 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
     auto resolve_hits = [&](bool& fin) {
       while (k_next < a.K && !(t + TIME_EPS < ck_time(k_next))) {
         double* slot = a.cond + (k_next * SLOT) * VB + vb;
+        if constexpr (WIDE) {
+          double* ws = wcond + (size_t)k_next * wslot;
+          if (FIX) {
+            wide_store_factor(ws, 2);
+            wide_copy(ws + WSLOT, Wg, false);
+            if (k_next == a.K - 1) {
+              wide_store_factor(wcond, 1);
+              wide_store_L1(wcond, 0);
+              wide_copy(wcond + WSLOT, nullptr, true);
+              wide_copy(wcond + WSLOT + (size_t)N * wd, Wm, false);
+            }
+            wide_copy(Wg, nullptr, true);
+          } else {
+            wide_store_L1(ws, 0);
+            wide_copy(ws + WSLOT + (size_t)N * wd, Wm, false);
+          }
+        }
         if (FIX) {
           if (real) {
 #pragma unroll
@@ -767,7 +1031,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
         } else {
           store_state(slot);
         }
-        if (sub == 0) a.n_accepted[b * a.K + k_next] = n_acc;
+        if (leader) a.n_accepted[b * a.K + k_next] = n_acc;
         k_next += 1;
       }
       if (k_next >= a.K) fin = true;
@@ -786,6 +1050,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
       } else {
         commit_pending();
         if (FIX) bw_commit();
+        if (WIDE && !FIX) wide_copy(Wm, Wp, false);  // fixed-point: done by pass 3 of prediction B
         mode = MODE_STEP;
         resolve_hits(fin);
       }
@@ -817,8 +1082,10 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
 #pragma unroll
               for (int j = 0; j <= i; ++j) SPEND(2 + N * D + Lay::tri(i, j)) = L_new[i][j];
             }
+            wide_pass3(0, 0, true, nullptr, nullptr, 0);
             mode = MODE_INTERP_A;
           } else {
+            wide_pass3(1, FIX ? 1 : 0, false, nullptr, nullptr, 0);  // before bw_commit: needs the old G
             t = t1;
             sigma_state = sigma;
 #pragma unroll
@@ -845,6 +1112,16 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
       // "t_c -> previous checkpoint" and continues from (t_c, m_t, L_t, identity); the filter emits
       // the extrapolated marginal.
       double* slot = a.cond + (k_next * SLOT) * VB + vb;
+      if constexpr (WIDE) {
+        double* ws = wcond + (size_t)k_next * wslot;
+        if (FIX) {
+          wide_store_factor(ws, 0);
+          wide_pass3(2, 2, false, ws + WSLOT, nullptr, 0);  // before bw_reset: needs the running G
+        } else {
+          wide_store_L1(ws, 2);
+          wide_pass3(2, 0, false, nullptr, ws + WSLOT + (size_t)N * wd, 2);
+        }
+      }
       if (FIX) {
         store_cond(slot);
         bw_reset();
@@ -860,7 +1137,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
 #pragma unroll
         for (int j = 0; j <= i; ++j) SL(i, j) = L_ext[i][j];
       }
-      if (sub == 0) a.n_accepted[b * a.K + k_next] = n_acc;
+      if (leader) a.n_accepted[b * a.K + k_next] = n_acc;
       if (FIX) {
         mode = MODE_INTERP_B;
       } else {
@@ -872,6 +1149,17 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
       // the conditional "accepted state -> checkpoint"; it becomes the accepted state's backward
       // model.  At the last checkpoint the terminal marginal marginalise((m1, L1), bw_1t) is
       // left to the smoothing kernel: store its two ingredients in slot 0.
+      if constexpr (WIDE) {
+        const bool term = (k_next == a.K - 1);
+        const double t1p = SPEND(0);
+        const bool again = (k_next + 1 < a.K) && (t1p > ck_time(k_next + 1) + TIME_EPS);
+        if (term) {
+          wide_store_factor(wcond, 0);
+          wide_store_L1(wcond, 1);
+        }
+        wide_pass3(again ? 0 : 3, again ? 0 : 1, false, term ? wcond + WSLOT : nullptr,
+                   term ? wcond + WSLOT + (size_t)N * wd : nullptr, 3);
+      }
       if (k_next == a.K - 1) {
         store_cond(a.cond + vb);
         if (real) {
@@ -883,7 +1171,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
       after_checkpoint(finished);
     }
     if (finished) {
-      if (sub == 0) {
+      if (leader) {
         a.n_rejected[b] = n_rej;
         a.status[b] = st;
         if (st != 0)

@@ -16,6 +16,8 @@ struct SmoothArgs {
   long long B, K;
   int dv;              // lanes ("virtual members") per IVP: 1, or d for the lane-per-dimension kernels
   int chol_per_dim;    // marg_chol layout: 1 -> [B][K][d][N][N] (blockdiag), 0 -> [B][K][N][N]
+  int wide_d;          // wide (CTA-per-IVP) kernels: runtime ODE dimension, else 0
+  double* wide_mean;   // wide kernels: per-member mean scratch [B][3][n][d]
   const double* cond;  // [K][SLOT][B]
   const int32_t* status;
   double* u;           // [B][K][D]
@@ -144,6 +146,102 @@ __global__ void __launch_bounds__(128) pn_smooth_kernel(const SmoothArgs a) {
     }
     if (k == 0) break;
     if (FIX) marginalise_from_global<N, D>(m, L, a.cond + (k * SLOT) * VB + vb, VB);
+  }
+}
+
+// ---- wide (CTA-per-IVP) variant: n x n factor per thread (replicated), n x d means in global ---
+struct WideSmoothArgs {
+  long long B, K;
+  int d;
+  const double* cond;   // [B][K][wslot]
+  double* mean;         // [B][3][n][d] scratch: the first [n][d] block is reused as the running mean
+  const int32_t* status;
+  double* u;            // [B][K][d]
+  double* u_std;        // [B][K][d]
+  double* marg_mean;    // nullable [B][K][n][d]
+  double* marg_chol;    // nullable [B][K][n][n]
+};
+
+template <int N, int STRAT, int THREADS>
+__global__ void __launch_bounds__(THREADS) pn_wide_smooth_kernel(const WideSmoothArgs a) {
+  using Lay = Layout<N, 1>;
+  constexpr bool FIX = (STRAT == 1);
+  constexpr int WSLOT = Lay::BW + Lay::NT;
+  constexpr int OFF_G = 0;
+  const int tid = threadIdx.x, d = a.d;
+  const long long b = blockIdx.x;
+  if (b >= a.B) return;
+  const long long wslot = (long long)WSLOT + 2LL * N * d;
+  const double* base = a.cond + (size_t)b * a.K * wslot;
+  double* rm = a.mean + (size_t)b * 3 * N * d;  // running mean [n][d]
+  const bool ok = (a.status[b] == 0);
+  const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+  double mdummy[N][1], L[N][N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) mdummy[i][0] = 0.0;
+  auto load_L1 = [&](const double* slot) {
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int j = 0; j <= i; ++j) L[i][j] = slot[Lay::BW + Lay::tri(i, j)];
+  };
+  auto marginalise_mean = [&](const double* slot) {  // rm[:, c] <- G rm[:, c] + g[:, c]
+    double G[N][N];
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int j = 0; j < N; ++j) G[i][j] = slot[OFF_G + i * N + j];
+    const double* g = slot + WSLOT;
+    for (int c = tid; c < d; c += THREADS) {
+      double mi[N], mo[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) mi[i] = rm[(size_t)i * d + c];
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        double acc = g[(size_t)i * d + c];
+#pragma unroll
+        for (int k = 0; k < N; ++k) acc = fma(G[i][k], mi[k], acc);
+        mo[i] = acc;
+      }
+#pragma unroll
+      for (int i = 0; i < N; ++i) rm[(size_t)i * d + c] = mo[i];
+    }
+  };
+  if (FIX) {
+    for (int e = tid; e < N * d; e += THREADS) rm[e] = base[WSLOT + (size_t)N * d + e];
+    load_L1(base);
+    __syncthreads();
+    marginalise_mean(base);
+    marginalise_from_global<N, 1>(mdummy, L, base, 1);
+    __syncthreads();
+  }
+  for (long long k = a.K - 1; k >= 0; --k) {
+    const double* slot = base + (size_t)k * wslot;
+    if (!FIX) {
+      for (int e = tid; e < N * d; e += THREADS) rm[e] = slot[WSLOT + (size_t)N * d + e];
+      load_L1(slot);
+      __syncthreads();
+    }
+    const double sd = dsqrt(fma(L[0][0], L[0][0], 0.0));
+    for (int c = tid; c < d; c += THREADS) {
+      a.u[(b * a.K + k) * d + c] = ok ? rm[c] : nanv;
+      a.u_std[(b * a.K + k) * d + c] = ok ? sd : nanv;
+    }
+    if (a.marg_mean)
+      for (int e = tid; e < N * d; e += THREADS) a.marg_mean[(b * a.K + k) * N * d + e] = ok ? rm[e] : nanv;
+    if (a.marg_chol && tid == 0) {
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) a.marg_chol[((b * a.K + k) * N + i) * N + j] = ok ? ((j <= i) ? L[i][j] : 0.0) : nanv;
+    }
+    __syncthreads();
+    if (k == 0) break;
+    if (FIX) {
+      marginalise_mean(slot);
+      marginalise_from_global<N, 1>(mdummy, L, slot, 1);
+      __syncthreads();
+    }
   }
 }
 

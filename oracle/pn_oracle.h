@@ -75,8 +75,9 @@ typedef struct {
   int32_t num_params;
   /* Summation order of the two norms over the ODE dimensions (||z|| for the isotropic calibration
    * and the scaled error norm).  <= 1: ascending-index fma chain (what a thread-per-IVP kernel
-   * does).  G > 1 (power of two >= d): one square per lane, then a butterfly (xor 2^k) sum over G
-   * lanes with zero padding -- the order the lane-per-dimension CUDA kernels use.  Any order is a
+   * does).  G > 1 (power of two): lane l sums the squares of entries l, l+G, ... in order, then a
+   * butterfly (xor 2^k) inside each group of 32 lanes and the group sums added in order -- the order
+   * the lane-per-dimension (G <= 32) and CTA-per-IVP (G = 128) CUDA kernels use.  Any order is a
    * faithful restatement; this knob only exists so that comparisons can be bit-exact. */
   int32_t reduction_group;
 } pn_oracle_config;

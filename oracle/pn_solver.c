@@ -236,13 +236,22 @@ static double sum_squares(const engine *E, const double *v, int k) {
     for (int c = 0; c < k; ++c) acc = fma(v[c], v[c], acc);
     return acc;
   }
-  double lanes[64], next[64];
-  for (int l = 0; l < G; ++l) lanes[l] = (l < k) ? fma(v[l], v[l], 0.0) : 0.0;
-  for (int off = G / 2; off >= 1; off >>= 1) {
+  /* lane l accumulates the entries l, l+G, l+2G, ... in order (fma chain from 0); lanes are then
+   * summed by a butterfly inside each group of 32 and the group sums are added in order */
+  double lanes[4096], next[4096];
+  for (int l = 0; l < G; ++l) {
+    double acc = 0.0;
+    for (int c = l; c < k; c += G) acc = fma(v[c], v[c], acc);
+    lanes[l] = acc;
+  }
+  int W = G < 32 ? G : 32;
+  for (int off = W / 2; off >= 1; off >>= 1) {
     for (int l = 0; l < G; ++l) next[l] = lanes[l] + lanes[l ^ off];
     for (int l = 0; l < G; ++l) lanes[l] = next[l];
   }
-  return lanes[0];
+  double r = lanes[0];
+  for (int w = 1; w < G / W; ++w) r = r + lanes[w * W];
+  return r;
 }
 
 /* predicted mean: m_p = pinv*m, m_ext_p = A m_p, m_ext = p*m_ext_p */

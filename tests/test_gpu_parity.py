@@ -357,3 +357,40 @@ def test_dense_filter_strategy_and_ekf0_vs_ekf1_accuracy(cabi, oracle):
     ekf0 = cabi.solve_host(_desc(cabi, "rigid_body", 3, 4, 1, 1, 5, fact="isotropic", corr="ts0", **kw), u0[None], par, None, save_at, None)
     for sol in (ekf0, ekf1):
         assert np.abs(sol["u"][0] - ref).max() < 1e-4
+
+
+# ---- CTA-per-IVP wide kernel: Brusselator with a runtime grid size (d = 2N) -----------------------
+@pytest.mark.parametrize("N,K,tol", [(20, 40, 1e-6), (32, 200, 1e-8), (100, 12, 1e-5)])
+def test_wide_brusselator_bitwise_vs_oracle(cabi, oracle, goldens, N, K, tol):
+    d = 2 * N
+    save_at = np.linspace(0.0, 10.0, K)
+    u0 = pu.brusselator_u0(N)
+    B = 3
+    alpha = np.array([1.0 / 50.0, 0.03, 0.012])
+    kw = dict(atol=tol, rtol=tol, dt0=0.01, P=1)
+    gpu = cabi.solve_host(_desc(cabi, "brusselator", d, 4, 1, B, K, **kw), np.tile(u0[None], (B, 1, 1)), alpha[:, None], None, save_at, None, full=True)
+    ocfg = _ocfg(oracle, "brusselator", d, 4, 1, reduction_group=128, **kw)
+    for b in range(B):
+        ora = oracle.solve_save_at(ocfg, u0, [alpha[b]], save_at, full=True)
+        assert ora["status"] == 0
+        _assert_bitwise({k: v[b] for k, v in gpu.items()}, ora)
+        np.testing.assert_array_equal(gpu["marg_mean"][b].reshape(K, -1), ora["marg_mean"].reshape(K, -1))
+        np.testing.assert_array_equal(gpu["marg_chol"][b].reshape(K, -1), ora["marg_chol"].reshape(K, -1))
+    if N == 32:
+        # experiments/4_brusselator/run.py: N = 32 took 12,425 steps; ulp-chaotic at the 1 % level
+        want = int(goldens["brusselator_num_steps_checkpoint"][list(goldens["brusselator_N"]).index(32)])
+        assert abs(int(gpu["n_accepted"][0, -1]) - want) <= 0.02 * want
+        np.testing.assert_allclose(gpu["u"][0], goldens["brusselator_ys_N32"], rtol=0, atol=5e-8)
+
+
+def test_wide_brusselator_terminal_values_and_filter(cabi, oracle):
+    # solve_adaptive_terminal_values (run.py:82-90) = two checkpoints; also the filter strategy
+    N = 24
+    u0 = pu.brusselator_u0(N)
+    for strat in ("fixedpoint", "filter"):
+        kw = dict(atol=1e-6, rtol=1e-6, dt0=0.01, P=1, strat=strat)
+        save_at = np.array([0.0, 2.0]) if strat == "fixedpoint" else np.linspace(0, 2.0, 9)
+        K = len(save_at)
+        gpu = cabi.solve_host(_desc(cabi, "brusselator", 2 * N, 4, 1, 1, K, **kw), u0[None], np.array([[0.02]]), None, save_at, None)
+        ora = oracle.solve_save_at(_ocfg(oracle, "brusselator", 2 * N, 4, 1, reduction_group=128, **kw), u0, [0.02], save_at)
+        _assert_bitwise({k: v[0] for k, v in gpu.items()}, ora)
