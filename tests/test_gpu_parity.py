@@ -394,3 +394,14 @@ def test_wide_brusselator_terminal_values_and_filter(cabi, oracle):
         gpu = cabi.solve_host(_desc(cabi, "brusselator", 2 * N, 4, 1, 1, K, **kw), u0[None], np.array([[0.02]]), None, save_at, None)
         ora = oracle.solve_save_at(_ocfg(oracle, "brusselator", 2 * N, 4, 1, reduction_group=128, **kw), u0, [0.02], save_at)
         _assert_bitwise({k: v[0] for k, v in gpu.items()}, ora)
+
+
+@pytest.mark.parametrize("N", [64, 128, 256])
+def test_wide_brusselator_reference_step_counts(cabi, goldens, N):
+    # experiments/4_brusselator/run.py:119-138 (data_checkpoint.npy "num_steps"): 48,233 / 190,024 / 754,285
+    K = 200
+    desc = _desc(cabi, "brusselator", 2 * N, 4, 1, 1, K, atol=1e-8, rtol=1e-8, dt0=0.01, P=1)
+    gpu = cabi.solve_host(desc, pu.brusselator_u0(N)[None], np.array([[1.0 / 50.0]]), None, np.linspace(0.0, 10.0, K), None)
+    want = int(goldens["brusselator_num_steps_checkpoint"][list(goldens["brusselator_N"]).index(N)])
+    assert int(gpu["status"][0]) == 0
+    assert int(gpu["n_accepted"][0, -1]) == want
