@@ -1,0 +1,121 @@
+"""GPU tests of the reference-facing Python API (the calls the reference's scripts and test make)."""
+
+import numpy as np
+import pytest
+
+import problems_util as pu
+
+pytestmark = pytest.mark.gpu
+
+
+def test_reference_test_case_logistic_checkpoint_solver():
+    # tests/test_ivpsolvers.py:31-52 of the reference, with the closed form in place of diffrax
+    from odecheckpts_b200 import ivps, ivpsolvers
+
+    vf, u0, time_span, args = ivps.logistic()
+    dt0, atol, rtol = 0.1, 1e-3, 1e-3
+    save_at = np.linspace(*time_span, num=5)
+    for method in ("ts0-2", "ts0-4"):
+        solve1 = ivpsolvers.solve(method, vf, u0[0], save_at, dt0=dt0, atol=atol, rtol=rtol)
+        solution1, aux1 = solve1(u0, args)
+        assert "u0_solve" in aux1.keys()
+        assert np.allclose(solution1[:, 0], pu.logistic_exact(save_at), atol=np.sqrt(atol), rtol=np.sqrt(rtol))
+
+
+def test_run_harder_style_pleiades_call():
+    # experiments/3_workprec_harder/run_harder.py:42-60
+    import scipy.integrate
+
+    from odecheckpts_b200 import ivps, ivpsolvers
+
+    vf_2nd, u0_2nd, (t0, t1) = ivps.pleiades_2nd()
+    xs = np.linspace(t0, t1, num=50)
+    tol = 1e-6 * 10
+    fun = ivpsolvers.solve("ts0-5", vf_2nd, u0_2nd[0], save_at=xs, dt0=0.1, atol=1e-3 * tol, rtol=tol, ode_order=2)
+    sol, aux = fun(u0_2nd, ())
+    assert sol.shape == (50, 14)
+
+    def f(t, y):
+        return np.concatenate([y[14:], vf_2nd(y[:14], y[14:], t=t)])
+
+    ref = scipy.integrate.solve_ivp(f, (t0, t1), np.concatenate(u0_2nd), t_eval=xs, method="DOP853", atol=1e-12, rtol=1e-12).y.T[:, :14]
+    assert np.linalg.norm(sol - ref) / np.sqrt(ref.size) < 1e-6
+    assert aux["solution"].num_steps[-1] > 500 and aux["solution"].status == 0
+
+
+def test_brusselator_script_style_builder_calls():
+    # experiments/4_brusselator/run.py:51-61,82-90,119-129 with the builder vocabulary
+    from odecheckpts_b200 import ivps
+    from odecheckpts_b200.probdiffeq import impl, ivpsolve, ivpsolvers, taylor
+
+    N = 40
+    vf, u0, (t0, t1), params = ivps.brusselator(N=N)
+    impl.impl.select("isotropic", ode_shape=(2 * N,))
+    num, tol = 4, 1e-6
+    ctrl = ivpsolve.control_proportional_integral()
+    ibm = ivpsolvers.prior_ibm(num_derivatives=num)
+    ts0 = ivpsolvers.correction_ts0(ode_order=1)
+    strategy = ivpsolvers.strategy_fixedpoint(ibm, ts0)
+    solver = ivpsolvers.solver_dynamic(strategy)
+    adaptive_solver = ivpsolve.adaptive(solver, atol=tol, rtol=tol, control=ctrl)
+    tcoeffs = taylor.odejet_unroll(lambda *y: vf(*y, t=t0, p=params), u0, num=num)
+    init = solver.initial_condition(tcoeffs, 1.0)
+    terminal = ivpsolve.solve_adaptive_terminal_values(vf, init, t0=t0, t1=t1, dt0=0.01, adaptive_solver=adaptive_solver)
+    save_at = np.linspace(t0, t1, num=200)
+    solution = ivpsolve.solve_adaptive_save_at(vf, init, save_at=save_at, dt0=0.01, adaptive_solver=adaptive_solver)
+    # no step clipping: both loops take the same number of steps
+    assert int(np.amax(solution.num_steps)) == int(terminal.num_steps)
+    assert solution.u.shape == (200, 2 * N) and solution.u_std.shape == (200, 2 * N)
+    np.testing.assert_allclose(solution.u[-1], terminal.u, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(solution.u[0], u0[0], atol=1e-13)
+    # the stats calls of src/odecheckpts/ivpsolvers.py:80-89
+    from odecheckpts_b200.probdiffeq import stats
+
+    post = stats.markov_select_terminal(solution.posterior)
+    margs = stats.markov_marginals(post, reverse=True)
+    mean = np.concatenate([margs.mean, solution.posterior.init.mean[[-1], ...]])
+    np.testing.assert_array_equal(mean[:, 0, :], solution.u)
+
+
+def test_vdp_script_style_dense_ekf1_filter_and_fixed_grid(goldens):
+    # experiments/1_van_der_pol/vdp.py:52-91
+    from odecheckpts_b200 import ivps
+    from odecheckpts_b200.probdiffeq import impl, ivpsolve, ivpsolvers, taylor
+
+    vf, (u0, du0), (t0, t1) = ivps.van_der_pol(mu=1e3)
+    impl.impl.select("dense", ode_shape=(1,))
+    num = 4
+    ibm = ivpsolvers.prior_ibm(num_derivatives=num)
+    ts1 = ivpsolvers.correction_ts1(ode_order=2)
+    strategy = ivpsolvers.strategy_filter(ibm, ts1)
+    solver = ivpsolvers.solver_dynamic(strategy)
+    tcoeffs = taylor.odejet_padded_scan(lambda *y: vf(*y, t=t0), [u0, du0], num=num - 1)
+    init = solver.initial_condition(tcoeffs, 1.0)
+    ctrl = ivpsolve.control_proportional_integral()
+    adaptive_solver = ivpsolve.adaptive(solver, atol=1e-3, rtol=1e-3, control=ctrl)
+    solution = ivpsolve.solve_adaptive_save_every_step(vf, init, t0=t0, t1=t1, dt0=0.01, adaptive_solver=adaptive_solver)
+    grid = goldens["vdp_grid"]
+    assert abs(len(solution.t) - len(grid)) <= 0.01 * len(grid) and solution.t[-1] == t1
+    np.testing.assert_allclose(solution.t[:26], grid[:26], atol=2e-14)
+    replay = ivpsolve.solve_fixed_grid(vf, init, grid=solution.t, solver=solver)
+    # replaying t[k+1] - t[k] is not bit-identical to the adaptive dt (stiff: rounding is amplified)
+    rel = np.abs(replay.u[:-1, 0] - solution.u[:-1, 0]) / np.abs(solution.u[:-1, 0])
+    assert np.median(rel) < 1e-7 and rel.max() < 1e-2
+
+
+def test_dense_ekf1_through_the_solve_factory_and_ensembles():
+    import torch
+
+    from odecheckpts_b200 import ivps, ivpsolvers
+
+    vf, u0, tspan, args = ivps.rigid_body(time_span=(0.0, 10.0))
+    save_at = np.linspace(*tspan, num=6)
+    kw = dict(save_at=save_at, dt0=0.1, atol=1e-8, rtol=1e-6)
+    s_iso, _ = ivpsolvers.solve("ts0-4", vf, u0[0], **kw)(u0, args)
+    s_dense, _ = ivpsolvers.solve("ts1-4", vf, u0[0], factorisation="dense", **kw)(u0, args)
+    s_bdiag, _ = ivpsolvers.solve("ts0-4", vf, u0[0], factorisation="blockdiag", **kw)(u0, args)
+    assert np.abs(s_iso - s_dense).max() < 1e-4 and np.abs(s_iso - s_bdiag).max() < 1e-4
+    B = 40
+    u0_b = torch.as_tensor(u0[0], device="cuda")[None] + 0.01 * torch.randn(B, 3, dtype=torch.float64, device="cuda")
+    s_b, aux = ivpsolvers.solve("ts1-4", vf, u0[0], factorisation="dense", **kw)((u0_b,), args)
+    assert s_b.is_cuda and tuple(s_b.shape) == (B, 6, 3) and int((aux["solution"].status != 0).sum()) == 0
