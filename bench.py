@@ -49,6 +49,9 @@ N_, D_ = NU + 1, 1
 W_ATTEMPT = 20.33 * (N_ * D_) ** 3 + (2 * N_ + 8 * D_) * (N_ * D_) ** 2 + 4 * (N_ * D_) * D_**2 + 8 + 8
 W_CHECKPOINT = 1.3 * W_ATTEMPT                      # two extra predictions + one marginalisation
 W_SWEEP_PER_K = 5.33 * N_**3 + 2 * N_**2 * D_       # one backward marginalisation
+# DRAM traffic of one solver-kernel launch on the headline workload (ncu, profiles/r01_scalar_kernel_final_ncu.txt):
+# 2.277 GB read + 3.493 GB written (the 1.7 GB of checkpoint conditionals + their partial-sector write-backs)
+NCU_DRAM_BYTES_PER_LAUNCH = 2.276631e9 + 3.493011e9
 
 
 def ensemble_inputs(first, count, stride=1):
@@ -327,7 +330,9 @@ def main():
                     "matches_device_path": e2e_ok},
             "roofline": {
                 "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-                "traffic": None, "kernel": "pn_scalar_kernel<VanDerPol,4,fixedpoint>", "kernel_ms": k_ms,
+                "traffic": NCU_DRAM_BYTES_PER_LAUNCH if B == MEMBERS else None,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, profiles/r01_scalar_kernel_final_ncu.txt",
+                "kernel": "pn_scalar_kernel<VanDerPol,4,fixedpoint>", "kernel_ms": k_ms,
                 "smooth_kernel_ms": float(np.mean(smooth_ms)),
                 "flops_per_attempt": W_ATTEMPT, "attempts_per_launch": attempts_rank,
                 "peak_source": "DFMA-chain microbenchmark in this run (pn_b200_measure_fp64_peak); MEASURED_PEAKS.json has no fp64 entry",

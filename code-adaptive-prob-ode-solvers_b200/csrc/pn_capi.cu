@@ -385,6 +385,15 @@ int pn_b200_solve_save_at_host(const pn_b200_desc* desc, const double* u0, const
       {&d_tl, nullptr, traj_len, rec ? B * 8 : 0},
       {&d_ws, nullptr, nullptr, ws_bytes},
   };
+  // keep freed blocks in the stream-ordered pool between calls (the default releases them at every
+  // synchronisation, which would re-map the multi-GB workspace on each solve)
+  {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ULL;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   cudaStream_t stream;
   ce = cudaStreamCreate(&stream);
   if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, cudaGetErrorString(ce));

@@ -154,8 +154,11 @@ struct Registrar {
 
 #define PN_CAT2(a, b) a##b
 #define PN_CAT(a, b) PN_CAT2(a, b)
+#ifndef PN_SCALAR_THREADS
+#define PN_SCALAR_THREADS 128
+#endif
 #define PN_REGISTER_SCALAR(Prob, NU, STRAT) \
-  static ::pn::Registrar PN_CAT(pn_reg_, __COUNTER__)(::pn::ScalarInstance<::pn::Prob, NU, STRAT, 1, 0, 128>::entry())
+  static ::pn::Registrar PN_CAT(pn_reg_, __COUNTER__)(::pn::ScalarInstance<::pn::Prob, NU, STRAT, 1, 0, PN_SCALAR_THREADS>::entry())
 #define PN_REGISTER_DENSE(Prob, NU, STRAT, WARPS) \
   static ::pn::Registrar PN_CAT(pn_reg_, __COUNTER__)(::pn::DenseInstance<::pn::Prob, NU, STRAT, WARPS>::entry())
 #define PN_REGISTER_WIDE(Prob, NU, STRAT) \

@@ -55,7 +55,8 @@ struct SolveArgs {
   const double* tol;      // nullable [B][2]
   const double* save_at;  // [K]
   const double* sigma0;   // nullable [B]
-  double* cond;           // workspace [K][E][B], slot 0 = terminal state
+  double* cond;           // workspace [B*dv][K][SLOT] (member-major: a lane's slot is contiguous, so its
+                          // stores fill whole 32-byte sectors); slot 0 = terminal state
   long long* n_accepted;  // [B][K]
   long long* n_rejected;  // [B]
   int32_t* status;        // [B]
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
   const bool real = WIDE ? false : (sub < DT);               // padding lanes carry no dimension; the wide
                                                              // mode has its own workspace stores
   const bool leader = WIDE ? (threadIdx.x == 0) : (sub == 0);  // writes the per-member counters
-  const long long VB = WIDE ? 1 : a.B * DV;                  // stride of the member-minor workspace
+  const long long VB = WIDE ? 1 : a.B * DV;                  // (member, owned dimension) pairs; trajectory stride
   // ---- wide mode: dimensions, per-member arrays, shared staging buffers ---------------------
   const int wd = WIDE ? a.wide_d : 0;                        // runtime ODE dimension
   const int wN = wd / 2;                                     // Brusselator grid points
@@ -391,9 +392,9 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
 #pragma unroll
           for (int i = 0; i < N; ++i) {
 #pragma unroll
-            for (int c = 0; c < D; ++c) a.cond[(long long)(i * D + c) * VB + vb] = SM(i, c);
+            for (int c = 0; c < D; ++c) a.cond[(long long)vb * a.K * SLOT + i * D + c] = SM(i, c);
 #pragma unroll
-            for (int j = 0; j <= i; ++j) a.cond[(long long)(N * D + Lay::tri(i, j)) * VB + vb] = 0.0;
+            for (int j = 0; j <= i; ++j) a.cond[(long long)vb * a.K * SLOT + N * D + Lay::tri(i, j)] = 0.0;
           }
         }
       } else {
@@ -943,19 +944,19 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
 #pragma unroll
       for (int i = 0; i < N; ++i) {
 #pragma unroll
-        for (int j = 0; j < N; ++j) dst[(long long)(OFF_G + i * N + j) * VB] = Gm[i][j];
+        for (int j = 0; j < N; ++j) dst[OFF_G + i * N + j] = Gm[i][j];
 #pragma unroll
-        for (int c = 0; c < D; ++c) dst[(long long)(OFF_g + i * D + c) * VB] = gm[i][c];
+        for (int c = 0; c < D; ++c) dst[OFF_g + i * D + c] = gm[i][c];
 #pragma unroll
-        for (int j = 0; j <= i; ++j) dst[(long long)(OFF_LAM + Lay::tri(i, j)) * VB] = Lm[i][j];
+        for (int j = 0; j <= i; ++j) dst[OFF_LAM + Lay::tri(i, j)] = Lm[i][j];
       }
     };
     auto store_identity_cond = [&](double* dst) {
       if (!real) return;
 #pragma unroll
-      for (int e = 0; e < Lay::BW; ++e) dst[(long long)e * VB] = 0.0;
+      for (int e = 0; e < Lay::BW; ++e) dst[e] = 0.0;
 #pragma unroll
-      for (int i = 0; i < N; ++i) dst[(long long)(OFF_G + i * N + i) * VB] = 1.0;
+      for (int i = 0; i < N; ++i) dst[OFF_G + i * N + i] = 1.0;
     };
     auto bw_commit = [&]() {  // running conditional <- merged result
 #pragma unroll
@@ -979,15 +980,15 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
 #pragma unroll
       for (int i = 0; i < N; ++i) {
 #pragma unroll
-        for (int c = 0; c < D; ++c) dst[(long long)(i * D + c) * VB] = mm[i][c];
+        for (int c = 0; c < D; ++c) dst[i * D + c] = mm[i][c];
 #pragma unroll
-        for (int j = 0; j <= i; ++j) dst[(long long)(N * D + Lay::tri(i, j)) * VB] = LL[i][j];
+        for (int j = 0; j <= i; ++j) dst[N * D + Lay::tri(i, j)] = LL[i][j];
       }
     };
     auto store_state = [&](double* dst) {  // committed hidden state (shared memory) -> workspace
       if (!real) return;
 #pragma unroll
-      for (int e = 0; e < Lay::MARG; ++e) dst[(long long)e * VB] = s_state[e * THREADS + tid];
+      for (int e = 0; e < Lay::MARG; ++e) dst[e] = s_state[e * THREADS + tid];
     };
     auto record = [&](double tt, const double (&mm)[N][D], const double (&LL)[N][N]) {
       if (GROUP == 1 && (a.flags & FLAG_RECORD) && n_acc < a.traj_cap) {
@@ -1000,7 +1001,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
     // exact hits on checkpoints by the committed state (m, L, running conditional): emit, reset
     auto resolve_hits = [&](bool& fin) {
       while (k_next < a.K && !(t + TIME_EPS < ck_time(k_next))) {
-        double* slot = a.cond + (k_next * SLOT) * VB + vb;
+        double* slot = a.cond + ((long long)vb * a.K + k_next) * SLOT;
         if constexpr (WIDE) {
           double* ws = wcond + (size_t)k_next * wslot;
           if (FIX) {
@@ -1021,11 +1022,11 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
         if (FIX) {
           if (real) {
 #pragma unroll
-            for (int e = 0; e < Lay::BW; ++e) slot[(long long)e * VB] = SBW(e);
+            for (int e = 0; e < Lay::BW; ++e) slot[e] = SBW(e);
           }
           if (k_next == a.K - 1) {
-            store_identity_cond(a.cond + vb);
-            store_state(a.cond + (long long)Lay::BW * VB + vb);
+            store_identity_cond(a.cond + (long long)vb * a.K * SLOT);
+            store_state(a.cond + (long long)vb * a.K * SLOT + Lay::BW);
           }
           bw_reset();
         } else {
@@ -1111,7 +1112,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
       // prediction "previous state -> checkpoint": fixed-point emits the merged conditional
       // "t_c -> previous checkpoint" and continues from (t_c, m_t, L_t, identity); the filter emits
       // the extrapolated marginal.
-      double* slot = a.cond + (k_next * SLOT) * VB + vb;
+      double* slot = a.cond + ((long long)vb * a.K + k_next) * SLOT;
       if constexpr (WIDE) {
         double* ws = wcond + (size_t)k_next * wslot;
         if (FIX) {
@@ -1161,10 +1162,10 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
                    term ? wcond + WSLOT + (size_t)N * wd : nullptr, 3);
       }
       if (k_next == a.K - 1) {
-        store_cond(a.cond + vb);
+        store_cond(a.cond + (long long)vb * a.K * SLOT);
         if (real) {
 #pragma unroll
-          for (int e = 0; e < Lay::MARG; ++e) a.cond[(long long)(Lay::BW + e) * VB + vb] = SPEND(2 + e);
+          for (int e = 0; e < Lay::MARG; ++e) a.cond[(long long)vb * a.K * SLOT + Lay::BW + e] = SPEND(2 + e);
         }
       }
       k_next += 1;

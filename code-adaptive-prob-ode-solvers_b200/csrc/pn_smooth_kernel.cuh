@@ -18,7 +18,7 @@ struct SmoothArgs {
   int chol_per_dim;    // marg_chol layout: 1 -> [B][K][d][N][N] (blockdiag), 0 -> [B][K][N][N]
   int wide_d;          // wide (CTA-per-IVP) kernels: runtime ODE dimension, else 0
   double* wide_mean;   // wide kernels: per-member mean scratch [B][3][n][d]
-  const double* cond;  // [K][SLOT][B]
+  const double* cond;  // [B*dv][K][SLOT]
   const int32_t* status;
   double* u;           // [B][K][D]
   double* u_std;       // [B][K][D]
@@ -112,19 +112,19 @@ __global__ void __launch_bounds__(128) pn_smooth_kernel(const SmoothArgs a) {
 #pragma unroll
     for (int i = 0; i < N; ++i) {
 #pragma unroll
-      for (int c = 0; c < D; ++c) m[i][c] = src[(long long)(i * D + c) * VB];
+      for (int c = 0; c < D; ++c) m[i][c] = src[i * D + c];
 #pragma unroll
-      for (int j = 0; j <= i; ++j) L[i][j] = src[(long long)(N * D + Lay::tri(i, j)) * VB];
+      for (int j = 0; j <= i; ++j) L[i][j] = src[N * D + Lay::tri(i, j)];
     }
   };
   if (FIX) {
     // terminal marginal = marginalise((m1, L1), bw_1t), both stored in slot 0
-    load_marg(a.cond + (long long)Lay::BW * VB + vb);
-    marginalise_from_global<N, D>(m, L, a.cond + vb, VB);
+    load_marg(a.cond + vb * a.K * SLOT + Lay::BW);
+    marginalise_from_global<N, D>(m, L, a.cond + vb * a.K * SLOT, 1);
   }
   const double nanv = __longlong_as_double(0x7ff8000000000000LL);
   for (long long k = a.K - 1; k >= 0; --k) {
-    if (!FIX) load_marg(a.cond + (k * SLOT) * VB + vb);
+    if (!FIX) load_marg(a.cond + (vb * a.K + k) * SLOT);
     const double sd = dsqrt(fma(L[0][0], L[0][0], 0.0));
 #pragma unroll
     for (int c = 0; c < D; ++c) {
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(128) pn_smooth_kernel(const SmoothArgs a) {
         for (int j = 0; j < N; ++j) a.marg_chol[(blk * N + i) * N + j] = ok ? ((j <= i) ? L[i][j] : 0.0) : nanv;
     }
     if (k == 0) break;
-    if (FIX) marginalise_from_global<N, D>(m, L, a.cond + (k * SLOT) * VB + vb, VB);
+    if (FIX) marginalise_from_global<N, D>(m, L, a.cond + (vb * a.K + k) * SLOT, 1);
   }
 }
 
