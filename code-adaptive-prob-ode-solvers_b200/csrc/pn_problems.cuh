@@ -151,7 +151,7 @@ struct VanDerPol {
 // ---- restricted three-body problem, second order (ivps.py:32-41; diffeqzoo) -------------
 struct ThreeBody {
   static constexpr int D = 2, Q = 2, P = 1, ID = 2;
-  static constexpr bool HAS_JAC = false;  // isotropic EKF0 only (measure.py:44-48)
+  static constexpr bool HAS_JAC = true;
   PN_DEV static void vf(const double* u, const double* par, double* f) {
     double mu = par[0], mp = 1.0 - mu;
     double x = u[0], y = u[1], xd = u[2], yd = u[3];
@@ -161,7 +161,23 @@ struct ThreeBody {
     f[0] = fma(-mu, b * p2, fma(-mp, a * p1, fma(2.0, yd, x)));
     f[1] = fma(-mu, y * p2, fma(-mp, y * p1, fma(-2.0, xd, y)));
   }
-  PN_DEV static void jac(const double*, const double*, double*) {}
+  // columns (x, y, x', y'); p = s^(-3/2), dp/d(a or y) = q (a or y) with q = -3 p / s
+  PN_DEV static void jac(const double* u, const double* par, double* J) {
+    double mu = par[0], mp = 1.0 - mu;
+    double x = u[0], y = u[1];
+    double a = x + mu, b = x - mp;
+    double s1 = fma(y, y, a * a), s2 = fma(y, y, b * b);
+    double p1 = inv_pow32(s1), p2 = inv_pow32(s2);
+    double q1 = (-3.0 * p1) * rcp(s1), q2 = (-3.0 * p2) * rcp(s2);
+    J[0] = 1.0 - fma(mu, fma(b * b, q2, p2), mp * fma(a * a, q1, p1));
+    J[1] = -fma(mu, (b * y) * q2, mp * ((a * y) * q1));
+    J[2] = 0.0;
+    J[3] = 2.0;
+    J[4] = J[1];
+    J[5] = 1.0 - fma(mu, fma(y * y, q2, p2), mp * fma(y * y, q1, p1));
+    J[6] = -2.0;
+    J[7] = 0.0;
+  }
   template <int N>
   PN_DEV static void vf_jet(const double* U, const double* par, double* F) {
     double mu = par[0], mp = 1.0 - mu;

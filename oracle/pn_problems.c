@@ -146,7 +146,7 @@ void pn_oracle_jac(int problem, int d, const double *u, double t, const double *
       double a = x + mu, b = x - mp;
       double s1 = fma(y, y, a * a), s2 = fma(y, y, b * b);
       double p1 = inv_pow32(s1), p2 = inv_pow32(s2);
-      double q1 = (-3.0 * p1) / s1, q2 = (-3.0 * p2) / s2; /* dp/d(a or y) = q * (a or y) */
+      double q1 = (-3.0 * p1) * (1.0 / s1), q2 = (-3.0 * p2) * (1.0 / s2); /* dp/d(a or y) = q * (a or y) */
       /* row 0: d/dx, d/dy, d/dx', d/dy' */
       jac[0] = 1.0 - fma(mu, fma(b * b, q2, p2), mp * fma(a * a, q1, p1));
       jac[1] = -fma(mu, (b * y) * q2, mp * ((a * y) * q1));

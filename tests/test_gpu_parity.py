@@ -405,3 +405,46 @@ def test_wide_brusselator_reference_step_counts(cabi, goldens, N):
     want = int(goldens["brusselator_num_steps_checkpoint"][list(goldens["brusselator_N"]).index(N)])
     assert int(gpu["status"][0]) == 0
     assert int(gpu["n_accepted"][0, -1]) == want
+
+
+MORE_ORDER_CASES = [
+    ("rigid_body", 3, 3, 1, 3, pu.RIGID_BODY_PARAMS, pu.rigid_body_u0, np.linspace(0, 50, 5), 0, dict(atol=1e-8, rtol=1e-5, dt0=50.0)),
+    ("rigid_body", 3, 5, 1, 3, pu.RIGID_BODY_PARAMS, pu.rigid_body_u0, np.linspace(0, 50, 5), 0, dict(atol=1e-10, rtol=1e-7, dt0=50.0)),
+    ("three_body", 2, 2, 2, 1, (pu.THREE_BODY_MU,), pu.three_body_u0, np.linspace(0, pu.THREE_BODY_T, 20), 0, dict(atol=1e-4, rtol=1e-4)),
+    ("three_body", 2, 5, 2, 1, (pu.THREE_BODY_MU,), pu.three_body_u0, np.linspace(0, pu.THREE_BODY_T, 20), 0, dict(atol=1e-8, rtol=1e-8)),
+    ("three_body", 2, 4, 2, 1, (pu.THREE_BODY_MU,), pu.three_body_u0, np.linspace(0, pu.THREE_BODY_T, 20), 0, dict(atol=1e-6, rtol=1e-6, fact="dense", corr="ts1")),
+    ("lotka_volterra", 2, 3, 1, 4, (0.5, 0.05, 0.5, 0.05), lambda: np.array([[20.0, 20.0]]), np.linspace(0, 20, 30), 0, dict(atol=1e-5, rtol=1e-5, dt0=0.1)),
+    ("logistic", 1, 5, 1, 2, (1.0, 1.0), lambda: np.array([[0.1]]), np.linspace(0, 2.5, 9), 0, dict(atol=1e-8, rtol=1e-8, dt0=0.1)),
+    ("logistic", 1, 8, 1, 2, (1.0, 1.0), lambda: np.array([[0.1]]), np.linspace(0, 2.5, 9), 0, dict(atol=1e-9, rtol=1e-9, dt0=0.1)),
+    ("pleiades", 14, 8, 2, 0, (), pu.pleiades_u0, np.linspace(0, 3, 50), 16, dict(atol=1e-6, rtol=1e-3, dt0=0.1)),
+]
+
+
+@pytest.mark.parametrize("case", MORE_ORDER_CASES, ids=lambda c: f"{c[0]}-nu{c[2]}-{c[9].get('fact', 'isotropic')}")
+def test_more_prior_orders_bitwise_vs_oracle(cabi, oracle, case):
+    problem, d, nu, q, P, params, u0fn, save_at, group, kw = case
+    kw = dict(kw, P=P)
+    u0 = u0fn()
+    K = len(save_at)
+    par = np.asarray([params], dtype=float) if P else None
+    gpu = cabi.solve_host(_desc(cabi, problem, d, nu, q, 1, K, **kw), u0[None], par, None, save_at, None)
+    ora = oracle.solve_save_at(_ocfg(oracle, problem, d, nu, q, reduction_group=group, **kw), u0, params, save_at)
+    assert ora["status"] == 0
+    _assert_bitwise({k: v[0] for k, v in gpu.items()}, ora)
+
+
+def test_pleiades_prob8_golden_rmse_on_gpu(cabi, oracle, goldens):
+    # Prob(8) of experiments/3_workprec_harder/run_harder.py:74-77, the three loosest tolerances
+    import scipy.integrate
+
+    xs = goldens["pleiades_checkpoints"]
+    y0 = pu.pleiades_u0()
+    f = lambda t, y: np.concatenate([y[14:], oracle.vf("pleiades", y.reshape(2, -1), [])])  # noqa: E731
+    ref = scipy.integrate.solve_ivp(f, (xs[0], xs[-1]), y0.ravel(), t_eval=xs, method="DOP853", atol=1e-13, rtol=1e-13).y.T[:, :14]
+    tols = goldens["pleiades_nu8_list_of_args"][:3] * 10
+    B = len(tols)
+    desc = _desc(cabi, "pleiades", 14, 8, 2, B, len(xs), dt0=0.1)
+    gpu = cabi.solve_host(desc, np.tile(y0[None], (B, 1, 1)), None, np.stack([1e-3 * tols, tols], 1), xs, None)
+    assert (gpu["status"] == 0).all()
+    rmse = np.linalg.norm((gpu["u"] - ref[None]).reshape(B, -1), axis=1) / np.sqrt(ref.size)
+    np.testing.assert_allclose(rmse, goldens["pleiades_nu8_precision"][:3], rtol=5e-3)
