@@ -1,0 +1,77 @@
+"""Full-size (BASELINE configs[1]: 65,536-member Van der Pol ensemble) checks through properties
+that need no oracle run: the oracle would take minutes at this size, the properties take one launch."""
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def full_run():
+    import torch
+
+    import bench
+    from odecheckpts_b200 import _cabi
+
+    B, K = bench.MEMBERS, bench.K_CHECKPOINTS
+    u0, par = bench.ensemble_inputs(0, B)
+    save_at = np.linspace(bench.T0, bench.T1, K)
+    desc = _cabi.Desc(5, 1, 4, 2, 2, 1, 1, 1, bench.TOL, bench.TOL, 0.01, 0.95, 0.2, 10.0, 0.3, 0.4, B, K, 0, 1, 0, 0)
+    dev = torch.device("cuda:0")
+    args = (torch.as_tensor(u0, device=dev), torch.as_tensor(par, device=dev), None, torch.as_tensor(save_at, device=dev), None)
+    out = _cabi.solve_device(desc, *args)
+    res = {k: v.cpu().numpy() for k, v in out.items() if not k.startswith("_")}
+    return _cabi, desc, u0, par, save_at, res
+
+
+def test_full_ensemble_is_healthy(full_run):
+    _, _, u0, _, _, res = full_run
+    assert (res["status"] == 0).all()
+    assert np.isfinite(res["u"]).all() and np.isfinite(res["u_std"]).all() and (res["u_std"] >= 0).all()
+    # accepted counts are cumulative over the checkpoints
+    assert (np.diff(res["n_accepted"], axis=1) >= 0).all() and (res["n_accepted"][:, 0] == 0).all()
+    acc = res["n_accepted"][:, -1]
+    assert 11000 < acc.min() and acc.max() < 20000 and 14500 < acc.mean() < 16000  # ~15.3k accepted per member
+    assert 500 < res["n_rejected"].mean() < 1500
+
+
+def test_smoothing_back_to_t0_reproduces_the_initial_values(full_run):
+    # marginalising the checkpoint Markov chain back to t0 returns u0 (a free self-check
+    # of every one of the 49 merged backward conditionals of every member)
+    _, _, u0, _, _, res = full_run
+    np.testing.assert_allclose(res["u"][:, 0, 0], u0[:, 0, 0], rtol=0, atol=1e-12)
+    assert res["u_std"][:, 0, 0].max() < 1e-6
+
+
+def test_members_do_not_depend_on_their_neighbours_or_the_schedule(full_run):
+    # solving a member alone, in a different slot, or in a second launch gives the same bits:
+    # the lane-level ticket queue makes the member->lane assignment timing dependent
+    import torch
+
+    _cabi, desc, u0, par, save_at, res = full_run
+    idx = np.array([0, 1, 31, 32, 4095, 37888, 65535])
+    d2 = _cabi.Desc(*[getattr(desc, n) for n, _ in _cabi.Desc._fields_])
+    d2.batch = len(idx)
+    sub = _cabi.solve_host(d2, u0[idx], par[idx], None, save_at, None)
+    for key in ("u", "u_std", "n_accepted", "n_rejected", "status"):
+        np.testing.assert_array_equal(sub[key], res[key][idx])
+    perm = np.random.default_rng(5).permutation(desc.batch)[:8192]
+    d3 = _cabi.Desc(*[getattr(desc, n) for n, _ in _cabi.Desc._fields_])
+    d3.batch = len(perm)
+    again = _cabi.solve_host(d3, u0[perm], par[perm], None, save_at, None)
+    np.testing.assert_array_equal(again["u"], res["u"][perm])
+    np.testing.assert_array_equal(again["n_rejected"], res["n_rejected"][perm])
+
+
+def test_solution_stays_on_the_limit_cycle_and_agrees_with_a_tighter_solve(full_run):
+    _cabi, desc, u0, par, save_at, res = full_run
+    assert np.abs(res["u"]).max() < 2.6  # |u| <= ~2.0 on the Van der Pol limit cycle, ICs within 2 +- 0.5
+    idx = np.arange(0, desc.batch, 4099)
+    d2 = _cabi.Desc(*[getattr(desc, n) for n, _ in _cabi.Desc._fields_])
+    d2.batch = len(idx)
+    d2.atol = d2.rtol = 1e-9
+    tight = _cabi.solve_host(d2, u0[idx], par[idx], None, save_at, None)
+    # away from the relaxation jumps (|u'| ~ 1e3) the 1e-6 solve is within ~1e-4 of the 1e-9 one
+    err = np.abs(tight["u"] - res["u"][idx])[:, :, 0]
+    assert np.median(err) < 1e-5 and np.quantile(err, 0.9) < 1e-3
