@@ -289,21 +289,6 @@ int pn_b200_solve_save_at(const pn_b200_desc* desc, const double* u0, const doub
   a.traj_cap = desc->traj_capacity;
   a.traj_len = (long long*)traj_len;
   prior_lq(desc->nu, a.lq);
-  // ticket quota: only for uniform tolerances (similar cost per member) and thread/lane-group kernels
-  a.quota_full = -1;
-  a.quota_warps = 0;
-  if (!tol && (p.k->family == FAMILY_SCALAR || p.k->family == FAMILY_GROUP_ISO || p.k->family == FAMILY_GROUP_BDIAG)) {
-    const long long per_warp = 32 / p.k->group, warps = p.k->threads / 32;
-    const long long slots = (long long)p.grid * warps * per_warp;
-    const long long full = desc->batch / slots, rem = desc->batch - full * slots;
-    if (full >= 1 && full <= 3 && rem > 0) {
-      long long elig = (rem + (long long)p.grid * per_warp - 1) / ((long long)p.grid * per_warp);
-      if (elig < warps) {
-        a.quota_full = full;
-        a.quota_warps = (int)elig;
-      }
-    }
-  }
 
   cudaError_t ce = cudaMemsetAsync(workspace, 0, p.ws_ticket, stream);
   if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, cudaGetErrorString(ce));

@@ -71,12 +71,6 @@ struct SolveArgs {
   // [B][3][n][d] (state mean, backward-conditional offset g, pending mean) in global memory
   int wide_d;
   double* wide_mean;
-  // Ticket quota (uniform-cost ensembles whose size is not a multiple of the resident lanes): every
-  // lane may take `quota_full` members; one more only in the first `quota_warps` warps of each CTA.
-  // This packs the last, partial wave into full warps spread evenly over the SMs instead of leaving
-  // every warp partially filled.  quota_full < 0: no quota (pure first-come-first-served).
-  long long quota_full;
-  int quota_warps;
   // Prior constant: lower Cholesky factor of the flipped Hilbert matrix, row-major
   // n x n, computed by the host (pn_capi.cu).  Kernel parameters live in the constant bank, so
   // DFMA reads these entries as immediate constant operands.
@@ -256,7 +250,6 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
 
   // ---- per-lane persistent state --------------------------------------------------------
   bool have = false, exhausted = false;
-  long long taken = 0;  // members this lane (group) has taken so far
   long long b = 0, vb = 0;
   double t = 0.0, dt_next = 0.0, e_prev = 1.0, sigma_state = 1.0, sigma0 = 1.0;
   double atol = a.atol, rtol = a.rtol;
@@ -270,9 +263,6 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
 
   for (;;) {
     // ---- fetch a member ----------------------------------------------------------------
-    if (!have && !exhausted && a.quota_full >= 0 &&
-        !(taken < a.quota_full || (taken == a.quota_full && (int)(threadIdx.x >> 5) < a.quota_warps)))
-      exhausted = true;
     if (!have && !exhausted) {
       unsigned long long tk = 0;
       if constexpr (WIDE) {
@@ -287,7 +277,6 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
       }
       if (tk < (unsigned long long)a.B) {
         b = (long long)tk;
-        taken += 1;
         vb = WIDE ? 0 : (b * DV + ((GROUP > 1 && real) ? sub : 0));
         have = true;
         double u0[Q * DT];
