@@ -343,7 +343,7 @@ def main():
         }  # fmt: skip
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            sample = int(min(B, max(256, 160 * cores)))  # ~10-20 s of CPU work
+            sample = int(min(B, max(512, 640 * cores)))  # ~10-20 s of CPU work
             rate, srate, secs = cpu_oracle_rate(sample, cores)
             line["cpu_baseline"] = {
                 "value": rate, "unit": UNIT, "cores": cores, "kind": "port", "accepted_steps_per_s": srate, "seconds": secs,
