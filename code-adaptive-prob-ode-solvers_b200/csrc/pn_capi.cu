@@ -327,6 +327,31 @@ int pn_b200_solve_save_at(const pn_b200_desc* desc, const double* u0, const doub
   return PN_B200_SUCCESS;
 }
 
+int pn_b200_markov_sample(const pn_b200_desc* desc, const void* workspace, size_t workspace_bytes,
+                          const int32_t* status, uint64_t seed, int64_t num_samples, double* samples,
+                          void* cuda_stream) {
+  Plan p;
+  int rc = make_plan(desc, &p, false);
+  if (rc) return rc;
+  if (desc->strategy != PN_B200_FIXEDPOINT || !p.k->launch_sample)
+    return fail(PN_B200_ERR_UNSUPPORTED, "posterior sampling needs a fixed-point solve of the thread-per-IVP or lane-per-dimension family");
+  if (!workspace || workspace_bytes < p.ws_ticket + p.ws_cond || !samples || !status || num_samples < 1)
+    return fail(PN_B200_ERR_ARGUMENT, "bad sampling arguments");
+  if (desc->batch == 0) return PN_B200_SUCCESS;
+  SampleArgs a;
+  a.B = desc->batch;
+  a.K = desc->num_save_at;
+  a.S = num_samples;
+  a.dv = p.k->dv;
+  a.seed = seed;
+  a.cond = (const double*)((const char*)workspace + p.ws_ticket);
+  a.status = status;
+  a.samples = samples;
+  cudaError_t ce = p.k->launch_sample(a, (cudaStream_t)cuda_stream);
+  if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, std::string("sampling kernel launch: ") + cudaGetErrorString(ce));
+  return PN_B200_SUCCESS;
+}
+
 int pn_b200_set_profiling(int enable) {
   g_profiling = enable != 0;
   return PN_B200_SUCCESS;

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include "pn_dense_kernel.cuh"
+#include "pn_sample_kernel.cuh"
 #include "pn_scalar_kernel.cuh"
 #include "pn_smooth_kernel.cuh"
 
@@ -28,6 +29,7 @@ struct KernelEntry {
   const void* solve_func;
   cudaError_t (*launch_solve)(const SolveArgs&, int grid, size_t smem, cudaStream_t);
   cudaError_t (*launch_smooth)(const SmoothArgs&, cudaStream_t);
+  cudaError_t (*launch_sample)(const SampleArgs&, cudaStream_t);  // nullptr: family has no sampler yet
 };
 
 void register_kernel(const KernelEntry& e);
@@ -46,9 +48,15 @@ struct ScalarInstance {
     pn_smooth_kernel<NU + 1, DL, STRAT><<<grid, 128, 0, s>>>(a);
     return cudaGetLastError();
   }
+  static cudaError_t launch_sample(const SampleArgs& a, cudaStream_t s) {
+    const long long total = a.B * a.dv * a.S;
+    pn_sample_kernel<NU + 1, DL><<<(unsigned)((total + 127) / 128), 128, 0, s>>>(a);
+    return cudaGetLastError();
+  }
   static KernelEntry entry() {
     using Lay = Layout<NU + 1, DL>;
     KernelEntry e;
+    e.launch_sample = (STRAT == 1) ? &launch_sample : nullptr;
     e.family = (GROUP == 1) ? FAMILY_SCALAR : (BDIAG ? FAMILY_GROUP_BDIAG : FAMILY_GROUP_ISO);
     e.group = GROUP;
     e.dv = DV;
@@ -89,6 +97,7 @@ struct DenseInstance {
   }
   static KernelEntry entry() {
     KernelEntry e;
+    e.launch_sample = nullptr;
     e.family = FAMILY_DENSE;
     e.group = 32;
     e.dv = 1;
@@ -127,6 +136,7 @@ struct WideInstance {
   }
   static KernelEntry entry() {
     KernelEntry e;
+    e.launch_sample = nullptr;
     e.family = FAMILY_WIDE;
     e.group = THREADS;
     e.dv = 1;

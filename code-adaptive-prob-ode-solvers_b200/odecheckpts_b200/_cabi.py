@@ -81,6 +81,7 @@ EXPORTS = (
     "pn_b200_solve_save_at_host",
     "pn_b200_get_kernel_info",
     "pn_b200_measure_fp64_peak",
+    "pn_b200_markov_sample",
     "pn_b200_set_profiling",
     "pn_b200_get_last_timing",
     "pn_b200_last_error",
@@ -116,6 +117,8 @@ def lib():
         L.pn_b200_get_kernel_info.argtypes = [C.POINTER(Desc), C.POINTER(KernelInfo)]
         L.pn_b200_measure_fp64_peak.restype = C.c_int
         L.pn_b200_measure_fp64_peak.argtypes = [C.POINTER(C.c_double), vp]
+        L.pn_b200_markov_sample.restype = C.c_int
+        L.pn_b200_markov_sample.argtypes = [C.POINTER(Desc), vp, C.c_size_t, vp, C.c_uint64, C.c_int64, vp, vp]
         L.pn_b200_set_profiling.restype = C.c_int
         L.pn_b200_set_profiling.argtypes = [C.c_int]
         L.pn_b200_get_last_timing.restype = C.c_int
@@ -170,6 +173,23 @@ def last_timing():
     a, b = C.c_float(0), C.c_float(0)
     check(lib().pn_b200_get_last_timing(C.byref(a), C.byref(b)))
     return a.value, b.value
+
+
+def markov_sample_device(desc, workspace, status, seed, num_samples, stream=None):
+    """[B, S, K, d] joint samples (torch CUDA tensor) from the conditionals a finished solve left in `workspace`."""
+    import torch
+
+    dev = workspace.device
+    out = torch.empty((desc.batch, int(num_samples), desc.num_save_at, desc.d), dtype=torch.float64, device=dev)
+    s = torch.cuda.current_stream(dev) if stream is None else stream
+    with torch.cuda.device(dev):
+        rc = lib().pn_b200_markov_sample(
+            C.byref(desc), C.c_void_p(workspace.data_ptr()), C.c_size_t(workspace.numel() * workspace.element_size()),
+            C.c_void_p(status.data_ptr()), C.c_uint64(int(seed) & (2**64 - 1)), C.c_int64(int(num_samples)),
+            C.c_void_p(out.data_ptr()), C.c_void_p(s.cuda_stream),
+        )  # fmt: skip
+    check(rc)
+    return out
 
 
 def _np_ptr(a):

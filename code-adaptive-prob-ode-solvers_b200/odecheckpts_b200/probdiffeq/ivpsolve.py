@@ -151,7 +151,7 @@ def _make_desc(field, nu, fact, solver, atol, rtol, control, dt0, B, K, flags=0,
 
 
 def _solve(vf, init, save_at, adaptive_solver, dt0, *, factorisation, return_marginals, tol, max_attempts, device,
-           flags=0, traj_capacity=0):  # fmt: skip
+           flags=0, traj_capacity=0, keep_conditionals=False):  # fmt: skip
     save_np = np.asarray(save_at.detach().cpu() if _is_torch(save_at) else save_at, dtype=np.float64)
     if save_np.ndim != 1 or len(save_np) < 2 or not np.all(np.diff(save_np) > 0):
         raise ValueError("save_at must be a strictly increasing 1-d grid with at least two points")
@@ -159,12 +159,21 @@ def _solve(vf, init, save_at, adaptive_solver, dt0, *, factorisation, return_mar
     use_torch, B, batched, u0, par, tol, scale = _stack_members(inits, params, tol, init.output_scale, field.num_params)
     desc = _make_desc(field, nu, fact, adaptive_solver.solver, adaptive_solver.atol, adaptive_solver.rtol,
                       adaptive_solver.control, dt0, B, len(save_np), flags, traj_capacity, max_attempts)  # fmt: skip
-    if use_torch:
+    if use_torch or keep_conditionals:
         import torch
 
+        as_numpy = not use_torch
+        if as_numpy:  # keep the workspace on the device: run the device path, hand numpy back
+            dev = torch.device(f"cuda:{device or 0}")
+            u0, par, tol, scale = (None if x is None else torch.as_tensor(x, device=dev) for x in (u0, par, tol, scale))
         save_dev = torch.as_tensor(save_np, dtype=torch.float64, device=u0.device)
         out = _cabi.solve_device(desc, u0, par, tol, save_dev, scale, full=return_marginals)
         t_out = save_dev
+        if keep_conditionals:
+            out["_handle"] = (desc, out["_workspace"], out["status"], as_numpy, batched)
+        if as_numpy:
+            t_out = save_np
+            out = {k: (v.cpu().numpy() if hasattr(v, "cpu") and not k.startswith("_") else v) for k, v in out.items()}
     else:
         out = _cabi.solve_host(desc, u0, par, tol, save_np, scale, full=return_marginals, device=device or 0)
         t_out = save_np
@@ -178,7 +187,7 @@ def _solution(out, t_out, batched, return_marginals):
         marg = Normal(sel(out["marg_mean"]), sel(out["marg_chol"]))
         mm, mc = out["marg_mean"], out["marg_chol"]
         init = Normal(sel(mm[:, 1:]), sel(mc[:, 1:])) if batched else Normal(mm[0, 1:], mc[0, 1:])
-        post = MarkovSeq(init, marg)
+        post = MarkovSeq(init, marg, out.get("_handle"))
     return Solution(
         t=t_out, u=sel(out["u"]), u_std=sel(out["u_std"]), output_scale=None, marginals=marg, posterior=post,
         num_steps=sel(out["n_accepted"]), num_rejected=sel(out["n_rejected"]), status=sel(out["status"]),
@@ -186,11 +195,14 @@ def _solution(out, t_out, batched, return_marginals):
 
 
 def solve_adaptive_save_at(vf, initial_condition, save_at, adaptive_solver, dt0, *, factorisation=None,
-                           return_marginals=True, tol=None, max_attempts=0, device=None):  # fmt: skip
+                           return_marginals=True, tol=None, max_attempts=0, device=None, keep_conditionals=False):  # fmt: skip
     """Adaptive solve that returns the posterior at the checkpoints `save_at` with O(K) memory
     (fixed-point smoother) -- the reference's hot path (ivpsolvers.py:71-77)."""
+    if keep_conditionals and not return_marginals:
+        raise ValueError("keep_conditionals=True needs return_marginals=True (the posterior object carries the handle)")
     _, out, t_out, batched = _solve(vf, initial_condition, save_at, adaptive_solver, dt0, factorisation=factorisation,
-                                    return_marginals=return_marginals, tol=tol, max_attempts=max_attempts, device=device)  # fmt: skip
+                                    return_marginals=return_marginals, tol=tol, max_attempts=max_attempts, device=device,
+                                    keep_conditionals=keep_conditionals)  # fmt: skip
     return _solution(out, t_out, batched, return_marginals)
 
 

@@ -16,6 +16,7 @@ class Normal(NamedTuple):
 class MarkovSeq(NamedTuple):
     init: Normal          # marginals at checkpoints 1..K-1 (init.mean[-1] = terminal)
     marginals_all: Normal  # smoothed marginals at checkpoints 0..K-1
+    handle: object = None  # (descriptor, device workspace, device status) when the solve kept its conditionals
 
 
 def markov_select_terminal(posterior):
@@ -31,3 +32,28 @@ def markov_marginals(markov_seq, *, reverse):
         raise NotImplementedError("only the backward (reverse=True) factorisation is produced by the solver")
     allm = markov_seq.marginals_all
     return Normal(allm.mean[:-1], allm.cholesky[:-1])
+
+
+def markov_sample(key, markov_seq, *, shape, reverse):
+    """Joint samples from the checkpoint Markov sequence (experiments/5_vs_interpolation/measure.py:69-77).
+
+    `key` is an integer seed (jax PRNG keys cannot be reproduced: Philox4x32-10 + Box-Muller on the
+    device; the samples have the reference's distribution, not its bits).  Needs a solution computed
+    with ``solve_adaptive_save_at(..., keep_conditionals=True)``.  Returns ``((qoi, samples), (init, None))``
+    like probdiffeq: ``qoi`` [S, K-1, d] at t_0..t_{K-2} and ``init`` [S, d] at the terminal checkpoint;
+    ``samples`` is None (only the quantity of interest is materialised)."""
+    if not reverse:
+        raise NotImplementedError("only reverse=True (backward factorisation) is produced by the solver")
+    if markov_seq.handle is None:
+        raise ValueError("the solution did not keep its backward conditionals: pass keep_conditionals=True to the solve")
+    from .. import _cabi
+
+    desc, workspace, status, as_numpy, batched = markov_seq.handle
+    (num,) = shape if isinstance(shape, (tuple, list)) else (shape,)
+    seed = int(key) if not hasattr(key, "__len__") else int(sum(int(x) << (32 * i) for i, x in enumerate(key)))
+    out = _cabi.markov_sample_device(desc, workspace, status, seed, num)  # [B, S, K, d]
+    if as_numpy:
+        out = out.cpu().numpy()
+    if not batched:
+        out = out[0]
+    return (out[..., :-1, :], None), (out[..., -1, :], None)

@@ -107,6 +107,18 @@ int pn_b200_solve_save_at_host(const pn_b200_desc* desc, const double* u0, const
                                int64_t* n_accepted, int64_t* n_rejected, int32_t* status, double* traj_t,
                                double* traj_u, double* traj_std, int64_t* traj_len, int device);
 
+/*
+ * Joint samples from the checkpoint Markov sequence of a FINISHED fixed-point solve:
+ * stats.markov_sample(key, posterior, shape=(S,), reverse=True), experiments/5_vs_interpolation/measure.py:69-77.
+ * `workspace` / `status` are the buffers the solve call used (the K backward conditionals are read
+ * from the workspace); samples: [B][S][K][d] draws of the ODE solution at the checkpoints (DEVICE).
+ * Random numbers are Philox4x32-10 + Box-Muller keyed by `seed`: same distribution as the reference,
+ * not the same bits as jax.random.  Thread-per-IVP and lane-per-dimension kernel families.
+ */
+int pn_b200_markov_sample(const pn_b200_desc* desc, const void* workspace, size_t workspace_bytes,
+                          const int32_t* status, uint64_t seed, int64_t num_samples, double* samples,
+                          void* cuda_stream);
+
 /* Launch geometry and compiled resource usage of the kernel that serves `desc` (for reports). */
 typedef struct {
   int32_t threads_per_cta, ctas_per_sm, num_sms, grid;

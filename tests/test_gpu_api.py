@@ -119,3 +119,45 @@ def test_dense_ekf1_through_the_solve_factory_and_ensembles():
     u0_b = torch.as_tensor(u0[0], device="cuda")[None] + 0.01 * torch.randn(B, 3, dtype=torch.float64, device="cuda")
     s_b, aux = ivpsolvers.solve("ts1-4", vf, u0[0], factorisation="dense", **kw)((u0_b,), args)
     assert s_b.is_cuda and tuple(s_b.shape) == (B, 6, 3) and int((aux["solution"].status != 0).sum()) == 0
+
+
+def test_posterior_sampling_matches_the_smoothed_marginals():
+    # experiments/5_vs_interpolation/measure.py:44-77: three-body, isotropic EKF0 o2 nu=4 uncalibrated,
+    # checkpoint solver + stats.markov_sample(reverse=True); parity here is distributional
+    from odecheckpts_b200 import ivps
+    from odecheckpts_b200.probdiffeq import impl, ivpsolve, ivpsolvers, stats, taylor
+
+    vf, init, tspan = ivps.three_body_restricted()
+    impl.impl.select("isotropic", ode_shape=(2,))
+    ibm = ivpsolvers.prior_ibm(num_derivatives=4)
+    ts0 = ivpsolvers.correction_ts0(ode_order=2)
+    strategy = ivpsolvers.strategy_fixedpoint(ibm, ts0)
+    solver = ivpsolvers.solver(strategy)
+    ctrl = ivpsolve.control_proportional_integral()
+    t0, t1 = tspan
+    tcoeffs = taylor.odejet_padded_scan(lambda *y: vf(*y, t=t0), init, num=3)
+    ic = solver.initial_condition(tcoeffs, np.ones(()))
+    asolver = ivpsolve.adaptive(solver, atol=1e-4, rtol=1e-4, control=ctrl)
+    save_at = np.linspace(t0, t1)
+    solution = ivpsolve.solve_adaptive_save_at(vf, ic, save_at=save_at, dt0=0.01, adaptive_solver=asolver, keep_conditionals=True)
+    assert int(solution.num_steps[-1]) == 448  # the reference's golden count at tol 1e-4
+    posterior = stats.markov_select_terminal(solution.posterior)
+    S = 20000
+    (qoi, _), (init_s, _) = stats.markov_sample(1, posterior, shape=(S,), reverse=True)
+    qoi = np.concatenate([qoi, init_s[..., None, :]], axis=-2)  # measure.py:76
+    assert qoi.shape == (S, len(save_at), 2)
+    mean, std = qoi.mean(axis=0), qoi.std(axis=0)
+    # sample moments vs the smoothed marginals: 5 standard errors (+ a floor for the exactly-known t0)
+    se = solution.u_std / np.sqrt(S)
+    assert np.all(np.abs(mean - solution.u) <= 5 * se + 1e-12)
+    big = solution.u_std > 1e-10
+    np.testing.assert_allclose(std[big], solution.u_std[big], rtol=0.05)
+    # joint structure: neighbouring checkpoints are strongly correlated draws of one trajectory
+    k = len(save_at) // 2
+    c = np.corrcoef(qoi[:, k, 0] - mean[k, 0], qoi[:, k + 1, 0] - mean[k + 1, 0])[0, 1]
+    assert abs(c) > 0.2
+    # a different key gives different draws, the same key the same draws
+    (q2, _), _ = stats.markov_sample(2, posterior, shape=(8,), reverse=True)
+    (q3, _), _ = stats.markov_sample(2, posterior, shape=(8,), reverse=True)
+    np.testing.assert_array_equal(q2, q3)
+    assert not np.array_equal(q2, qoi[:8, :-1])
