@@ -39,8 +39,9 @@ PN_DEV void matmul(const double* A, int lda, const double* B, int ldb, double* C
 }
 
 // Householder QR, R only (oracle/pn_linalg.c: pn_qr_r).  M is rows x cols with leading dimension ld.
-PN_DEV void qr_r(double* M, int ld, int rows, int cols, int lane) {
-  const int kmax = rows < cols ? rows : cols;
+PN_DEV void qr_r(double* M, int ld, int rows, int cols, int lane, int ncols = 1 << 30) {
+  int kmax = rows < cols ? rows : cols;
+  if (ncols < kmax) kmax = ncols;  // triangularise only the first ncols columns (pn_qr_r_partial)
   for (int j = 0; j < kmax; ++j) {
     double sigma2 = 0.0;
     for (int i = j + 1; i < rows; ++i) {
@@ -360,13 +361,13 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_kernel(const __grid_const
             M[(Dn + i) * W2 + Dn + j] = L_p[j * Dn + i];
           }
           __syncwarp();
-          wc::qr_r(M, W2, W2, W2, lane);
+          wc::qr_r(M, W2, W2, W2, lane, Dn);  // lower-right block stays full: see pn_scalar_kernel.cuh
           // X = RY^{-1} R12
           wc::solve_upper(M, W2, M + Dn, W2, X, Dn, Dn, Dn, lane);
           for (int e = lane; e < MAT; e += 32) {
             const int i = e / Dn, j = e - i * Dn;
             Gn[e] = (pv[i] * X[j * Dn + i]) * pinvv[j];
-            Ln[e] = (j <= i) ? pv[i] * M[(Dn + j) * W2 + Dn + i] : 0.0;
+            Ln[e] = pv[i] * M[(Dn + j) * W2 + Dn + i];
             L_ext[e] = (j <= i) ? pv[i] * M[j * W2 + i] : 0.0;
           }
           for (int i = lane; i < Dn; i += 32) {

@@ -632,26 +632,9 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
 #pragma unroll
         for (int j = 0; j <= i; ++j) L_ext[i][j] = p[i] * RY[j][i];
       if (FIX) {
-        // phase 2: QR of the (now full) bottom-right block
-#pragma unroll
-        for (int j = 0; j < N - 1; ++j) {
-          double sigma2 = 0.0;
-#pragma unroll
-          for (int i = j + 1; i < N; ++i) sigma2 = fma(BR[i][j], BR[i][j], sigma2);
-          Reflector rf = make_reflector(BR[j][j], sigma2);
-#pragma unroll
-          for (int c = j + 1; c < N; ++c) {
-            double w = 0.0;
-#pragma unroll
-            for (int i = j + 1; i < N; ++i) w = fma(BR[i][j], BR[i][c], w);
-            w = fma(rf.v0, BR[j][c], w);
-            double f = w * rf.g;
-            BR[j][c] = fma(-f, rf.v0, BR[j][c]);
-#pragma unroll
-            for (int i = j + 1; i < N; ++i) BR[i][c] = fma(-f, BR[i][j], BR[i][c]);
-          }
-          BR[j][j] = rf.beta;
-        }
+        // The lower-right block BR is NOT triangularised: BR^T is already a valid square-root factor
+        // of the backward noise (BR^T BR = R_XY^T R_XY) and the merge below re-triangularises anyway.
+        // That removes n-1 serial Householder chains per step.
         // X = RY^{-1} R12 (back substitution); G_p = X^T
 #pragma unroll
         for (int i = N - 1; i >= 0; --i) {
@@ -676,7 +659,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
 #pragma unroll
           for (int j = 0; j < N; ++j) Gn[i][j] = (p[i] * X[j][i]) * pinv[j];
 #pragma unroll
-          for (int j = 0; j <= i; ++j) Ln[i][j] = p[i] * BR[j][i];
+          for (int j = 0; j < N; ++j) Ln[i][j] = p[i] * BR[j][i];
         }
       }
     }
@@ -711,9 +694,9 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
       for (int i = 0; i < N; ++i)
 #pragma unroll
         for (int j = 0; j < N; ++j) {
-          double acc = G1[i][j] * Ln[j][j];
+          double acc = G1[i][0] * Ln[0][j];
 #pragma unroll
-          for (int k = j + 1; k < N; ++k) acc = fma(G1[i][k], Ln[k][j], acc);
+          for (int k = 1; k < N; ++k) acc = fma(G1[i][k], Ln[k][j], acc);
           Mt[j][i] = acc;
         }
       double Mb[N][N];  // Mb[i][j] = Lam_run[j][i], nonzero for i <= j

@@ -25,8 +25,14 @@
 /* On exit rows 0..min(rows,cols)-1 hold R (upper triangular), everything      */
 /* below the diagonal is zero.                                                 */
 /* ------------------------------------------------------------------------- */
-void pn_qr_r(double *M, int rows, int cols) {
+void pn_qr_r(double *M, int rows, int cols) { pn_qr_r_partial(M, rows, cols, cols); }
+
+/* The same, but only the first `ncols` columns are triangularised (all columns receive the
+ * reflectors).  The fixed-point predict only needs R_Y and R_12 of the 2N x 2N block matrix in
+ * triangular form; the lower-right block is used as a (non-triangular) square-root factor. */
+void pn_qr_r_partial(double *M, int rows, int cols, int ncols) {
   int kmax = rows < cols ? rows : cols;
+  if (ncols < kmax) kmax = ncols;
   for (int j = 0; j < kmax; ++j) {
     double sigma2 = 0.0;
     for (int i = j + 1; i < rows; ++i) sigma2 = fma(M[i * cols + j], M[i * cols + j], sigma2);

@@ -90,6 +90,7 @@ typedef struct {
   double *hL, *W, *Y, *Rm, *Rs;  /* r*N, N*r, ... */
   double *sig;                   /* F */
   double *keep1, *keep2, *gnew;  /* N*Ctot scratch */
+  double *idG, *idL, *idg;       /* identity conditional (I, 0, 0) */
 } engine;
 
 typedef struct {
@@ -162,6 +163,8 @@ static int engine_init(engine *E, const pn_oracle_config *cfg) {
   E->Rm = dalloc((size_t)N * E->r); E->Rs = dalloc((size_t)N * E->r);
   E->sig = dalloc(E->F);
   E->keep1 = dalloc(NC); E->keep2 = dalloc(NC); E->gnew = dalloc(NC);
+  E->idG = dalloc(NN); E->idL = dalloc(NN); E->idg = dalloc(NC);
+  for (int i = 0; i < N; ++i) E->idG[(size_t)i * N + i] = 1.0;
   return 0;
 }
 
@@ -170,7 +173,7 @@ static void engine_free(engine *E) {
   free(E->m_ext); free(E->z); free(E->err); free(E->fbuf); free(E->ubuf); free(E->h); free(E->jac);
   free(E->L_p); free(E->AL); free(E->M2); free(E->Gp); free(E->Lamp); free(E->X); free(E->T);
   free(E->Mq); free(E->L_ext); free(E->gain); free(E->hL); free(E->W); free(E->Y); free(E->Rm);
-  free(E->Rs); free(E->sig); free(E->keep1); free(E->keep2); free(E->gnew);
+  free(E->Rs); free(E->sig); free(E->keep1); free(E->keep2); free(E->gnew); free(E->idG); free(E->idL); free(E->idg);
 }
 
 static void pstate_alloc(const engine *E, pstate *S) {
@@ -353,7 +356,10 @@ static void predict_cov_one(engine *E, const double *L, double sigma, double *L_
       M[(N + i) * W2 + j] = AL[j * N + i];
       M[(N + i) * W2 + N + j] = L_p[j * N + i];
     }
-  pn_qr_r(M, W2, W2);
+  /* only the first N columns are triangularised: R_Y, R_12 are final after that, and the
+   * lower-right block B (N x N, full) satisfies B^T B = R_XY^T R_XY, i.e. B^T is a valid
+   * (non-triangular) square-root factor of the backward noise; the merge below re-triangularises */
+  pn_qr_r_partial(M, W2, W2, N);
   double *RY = E->Mq, *R12 = E->Gp, *X = E->X;
   for (int i = 0; i < N; ++i)
     for (int j = 0; j < N; ++j) {
@@ -367,7 +373,7 @@ static void predict_cov_one(engine *E, const double *L, double sigma, double *L_
   for (int i = 0; i < N; ++i)
     for (int j = 0; j < N; ++j) {
       Gn[i * N + j] = (E->p[i] * X[j * N + i]) * E->pinv[j];
-      Ln[i * N + j] = (j <= i) ? E->p[i] * M[(N + j) * W2 + N + i] : 0.0;
+      Ln[i * N + j] = E->p[i] * M[(N + j) * W2 + N + i];
     }
   double *gnew = E->gnew;
   for (int i = 0; i < N; ++i)
@@ -379,10 +385,9 @@ static void predict_cov_one(engine *E, const double *L, double sigma, double *L_
   for (int i = 0; i < N; ++i)
     for (int j = 0; j < N; ++j) L_ext[i * N + j] = (j <= i) ? E->p[i] * M[j * W2 + i] : 0.0;
   if (runG == NULL) {
-    memcpy(Go, Gn, sizeof(double) * N * N);
-    memcpy(Lo, Ln, sizeof(double) * N * N);
-    for (int i = 0; i < N; ++i)
-      for (int c = c0; c < c0 + C; ++c) go[i * Ct + c] = gnew[i * Ct + c];
+    /* running conditional = identity: still merge, so that Lam comes out triangular */
+    double *Gi = E->idG, *Li = E->idL, *gi = E->idg;
+    merge_one(E, Gi, gi, Li, Gn, gnew, Ln, Go, go, Lo, c0, C);
   } else {
     /* merge_one uses X, T, M2, m_p as scratch: Gn lives in AL, Ln in Lamp, gnew in its own buffer;
      * m_p is overwritten -> callers restore it per factor set. */
