@@ -21,15 +21,21 @@
 //     needs (MODE_INTERP_A: previous state -> checkpoint, MODE_INTERP_B: checkpoint -> accepted
 //     state).  Accept/reject and checkpoint handling only change which results a lane commits,
 //     so per-member step control costs predicated moves, not divergent code.
-//   * Hidden state (mean, Cholesky factor) lives in registers; the running backward conditional
-//     (G, g, Lam) and the accepted-but-uncommitted state of a lane that is interpolating are parked
-//     in shared memory ([element][thread], conflict free).
+//   * The step's working set (block-QR workspace, reflectors, new conditional) lives in registers;
+//     everything only read at the start of a step or written at commit -- hidden state (mean,
+//     Cholesky factor), running backward conditional (G, g, Lam), and the accepted-but-uncommitted
+//     state of a lane that is interpolating -- is parked in shared memory ([element][thread],
+//     conflict free).
+//   * Only the first n columns of the 2n x 2n fixed-point block matrix are triangularised; the
+//     lower-right block is used as a full square-root factor and the merge re-triangularises.
 //   * Lanes pull members from a global atomic ticket, so differing step counts (tolerance
 //     sweeps) never idle a lane while work remains.
-//   * HBM traffic: inputs once per member; per checkpoint one backward conditional
-//     ([checkpoint][element][member], member-minor so a warp's stores coalesce).
+//   * HBM traffic: inputs once per member; per checkpoint one backward conditional into the
+//     member-major workspace [member][checkpoint][element] (a lane's slot is contiguous, so its
+//     stores fill whole sectors even when the lanes of a warp cross checkpoints at different times).
 //   * The O(K) backward marginalisation (stats.markov_marginals(reverse=True),
 //     ivpsolvers.py:80-81) runs as a second, fully convergent kernel (pn_smooth_kernel).
+//   * GROUP > 1 / WIDE = 1 reuse the same step for lane-per-dimension and CTA-per-IVP mappings.
 //
 // Arithmetic order follows oracle/pn_solver.c exactly, skipping structural zeros only (which is
 // exact), so results are comparable bit for bit.
