@@ -50,8 +50,9 @@ W_ATTEMPT = 20.33 * (N_ * D_) ** 3 + (2 * N_ + 8 * D_) * (N_ * D_) ** 2 + 4 * (N
 W_CHECKPOINT = 1.3 * W_ATTEMPT                      # two extra predictions + one marginalisation
 W_SWEEP_PER_K = 5.33 * N_**3 + 2 * N_**2 * D_       # one backward marginalisation
 # DRAM traffic of one solver-kernel launch on the headline workload (ncu, profiles/r01_scalar_kernel_final_ncu.txt):
-# 2.277 GB read + 3.493 GB written (the 1.7 GB of checkpoint conditionals + their partial-sector write-backs)
-NCU_DRAM_BYTES_PER_LAUNCH = 2.276631e9 + 3.493011e9
+# 0.213 GB read + 1.286 GB written = the checkpoint conditionals of the fixed-point smoother
+# (65,536 members x 49 checkpoints x 65 doubles = 1.67 GB, part of it still in L2 at kernel end).
+NCU_DRAM_BYTES_PER_LAUNCH = 213.266944e6 + 1.285683e9
 
 
 def ensemble_inputs(first, count, stride=1):

@@ -32,19 +32,36 @@ PN_DEV void matmul(const double* A, int lda, const double* B, int ldb, double* C
   for (int e = lane; e < r * c; e += 32) {
     const int i = e / c, j = e - i * c;
     double acc = A[i * lda] * B[j];
+#pragma unroll 4
     for (int l = 1; l < k; ++l) acc = fma(A[i * lda + l], B[l * ldb + j], acc);
     C[i * ldc + j] = acc;
   }
   __syncwarp();
 }
 
-// Householder QR, R only (oracle/pn_linalg.c: pn_qr_r).  M is rows x cols with leading dimension ld.
-PN_DEV void qr_r(double* M, int ld, int rows, int cols, int lane, int ncols = 1 << 30) {
+// Householder QR, R only (oracle/pn_linalg.c: pn_qr_r / pn_qr_r_partial).  M is rows x cols with
+// leading dimension ld.  `shape` names the structural zeros of the stacked matrix so that the
+// loops skip them (exact: a zero entry contributes fma(0, x, acc) = acc in the oracle's full loops):
+//   QR_FULL            no structure
+//   QR_TOPTRI_BOTFULL  top nb x . block upper triangular (zero below its diagonal), bottom block full
+//   QR_TOPFULL_BOTTRI  top nb x . block full, bottom block upper triangular
+enum : int { QR_FULL = 0, QR_TOPTRI_BOTFULL = 1, QR_TOPFULL_BOTTRI = 2 };
+PN_DEV void qr_r(double* M, int ld, int rows, int cols, int lane, int ncols = 1 << 30, int shape = QR_FULL, int nb = 0) {
   int kmax = rows < cols ? rows : cols;
   if (ncols < kmax) kmax = ncols;  // triangularise only the first ncols columns (pn_qr_r_partial)
   for (int j = 0; j < kmax; ++j) {
+    // rows below the diagonal that can be non-zero in column j: [a0, a1) and [b0, b1)
+    int a0 = j + 1, a1 = rows, b0 = rows, b1 = rows;
+    if (shape == QR_TOPTRI_BOTFULL && j < nb) { a0 = nb; a1 = rows; }
+    if (shape == QR_TOPFULL_BOTTRI) { a0 = j + 1; a1 = nb; b0 = nb; b1 = nb + j + 1; }
     double sigma2 = 0.0;
-    for (int i = j + 1; i < rows; ++i) {
+#pragma unroll 4
+    for (int i = a0; i < a1; ++i) {
+      const double x = M[i * ld + j];
+      sigma2 = fma(x, x, sigma2);
+    }
+#pragma unroll 4
+    for (int i = b0; i < b1; ++i) {
       const double x = M[i * ld + j];
       sigma2 = fma(x, x, sigma2);
     }
@@ -56,15 +73,22 @@ PN_DEV void qr_r(double* M, int ld, int rows, int cols, int lane, int ncols = 1 
     const double g = rcp(norm * (fabs(alpha) + norm));
     for (int c = j + 1 + lane; c < cols; c += 32) {
       double w = 0.0;
-      for (int i = j + 1; i < rows; ++i) w = fma(M[i * ld + j], M[i * ld + c], w);
+#pragma unroll 4
+      for (int i = a0; i < a1; ++i) w = fma(M[i * ld + j], M[i * ld + c], w);
+#pragma unroll 4
+      for (int i = b0; i < b1; ++i) w = fma(M[i * ld + j], M[i * ld + c], w);
       w = fma(v0, M[j * ld + c], w);
       const double f = w * g;
       M[j * ld + c] = fma(-f, v0, M[j * ld + c]);
-      for (int i = j + 1; i < rows; ++i) M[i * ld + c] = fma(-f, M[i * ld + j], M[i * ld + c]);
+#pragma unroll 4
+      for (int i = a0; i < a1; ++i) M[i * ld + c] = fma(-f, M[i * ld + j], M[i * ld + c]);
+#pragma unroll 4
+      for (int i = b0; i < b1; ++i) M[i * ld + c] = fma(-f, M[i * ld + j], M[i * ld + c]);
     }
     __syncwarp();
     if (lane == 0) M[j * ld + j] = beta;
-    for (int i = j + 1 + lane; i < rows; i += 32) M[i * ld + j] = 0.0;
+    for (int i = a0 + lane; i < a1; i += 32) M[i * ld + j] = 0.0;
+    for (int i = b0 + lane; i < b1; i += 32) M[i * ld + j] = 0.0;
     __syncwarp();
   }
 }
@@ -346,7 +370,7 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_kernel(const __grid_const
             M[(Dn + i) * Dn + j] = AL[j * Dn + i];
           }
           __syncwarp();
-          wc::qr_r(M, Dn, W2, Dn, lane);
+          wc::qr_r(M, Dn, W2, Dn, lane, 1 << 30, wc::QR_TOPTRI_BOTFULL, Dn);
           for (int e = lane; e < MAT; e += 32) {
             const int i = e / Dn, j = e - i * Dn;
             L_ext[e] = (j <= i) ? pv[i] * M[j * Dn + i] : 0.0;
@@ -361,7 +385,7 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_kernel(const __grid_const
             M[(Dn + i) * W2 + Dn + j] = L_p[j * Dn + i];
           }
           __syncwarp();
-          wc::qr_r(M, W2, W2, W2, lane, Dn);  // lower-right block stays full: see pn_scalar_kernel.cuh
+          wc::qr_r(M, W2, W2, W2, lane, Dn, wc::QR_TOPTRI_BOTFULL, Dn);  // lower-right block stays full: see pn_scalar_kernel.cuh
           // X = RY^{-1} R12
           wc::solve_upper(M, W2, M + Dn, W2, X, Dn, Dn, Dn, lane);
           for (int e = lane; e < MAT; e += 32) {
@@ -391,7 +415,7 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_kernel(const __grid_const
             M[(Dn + i) * Dn + j] = S_Lam[j * Dn + i];
           }
           __syncwarp();
-          wc::qr_r(M, Dn, W2, Dn, lane);
+          wc::qr_r(M, Dn, W2, Dn, lane, 1 << 30, wc::QR_TOPFULL_BOTTRI, Dn);
           for (int e = lane; e < MAT; e += 32) {
             const int i = e / Dn, j = e - i * Dn;
             Lm[e] = (j <= i) ? M[j * Dn + i] : 0.0;
@@ -621,7 +645,7 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_smooth_kernel(const Smoot
       M[(Dn + i) * Dn + j] = Lam[j * Dn + i];
     }
     __syncwarp();
-    wc::qr_r(M, Dn, 2 * Dn, Dn, lane);
+    wc::qr_r(M, Dn, 2 * Dn, Dn, lane, 1 << 30, wc::QR_TOPFULL_BOTTRI, Dn);
     for (int e = lane; e < MAT; e += 32) {
       const int i = e / Dn, j = e - i * Dn;
       L[e] = (j <= i) ? M[j * Dn + i] : 0.0;
