@@ -448,3 +448,27 @@ def test_pleiades_prob8_golden_rmse_on_gpu(cabi, oracle, goldens):
     assert (gpu["status"] == 0).all()
     rmse = np.linalg.norm((gpu["u"] - ref[None]).reshape(B, -1), axis=1) / np.sqrt(ref.size)
     np.testing.assert_allclose(rmse, goldens["pleiades_nu8_precision"][:3], rtol=5e-3)
+
+
+def test_single_attempted_step_parity(cabi, oracle):
+    # SURVEY section 4, ladder item 1: one attempted step from the Taylor-initialised state, GPU vs
+    # the oracle's single-step entry point: mean, factor (L L^T), via a 2-point fixed grid (always accepted)
+    for problem, d, nu, q, params, u0, fact, corr, dt in [
+        ("van_der_pol", 1, 4, 2, (1e3,), pu.van_der_pol_u0(), "dense", "ts1", 1e-4),
+        ("rigid_body", 3, 4, 1, pu.RIGID_BODY_PARAMS, pu.rigid_body_u0(), "isotropic", "ts0", 0.05),
+        ("rigid_body", 3, 4, 1, pu.RIGID_BODY_PARAMS, pu.rigid_body_u0(), "dense", "ts1", 0.05),
+    ]:
+        P = len(params)
+        kw = dict(atol=1e-3, rtol=1e-3, dt0=dt, P=P, fact=fact, corr=corr, strat="filter")
+        desc = _desc(cabi, problem, d, nu, q, 1, 2, flags=cabi.FLAG_FIXED_GRID, **kw)
+        gpu = cabi.solve_host(desc, u0[None], np.asarray([params]), None, np.array([0.0, dt]), None, full=True)
+        ocfg = _ocfg(oracle, problem, d, nu, q, **kw)
+        m0 = oracle.taylor_init(problem, u0, nu, params)
+        n = nu + 1
+        dense = fact == "dense" and d > 1
+        N = n * d if dense else n
+        chol0 = np.zeros((1, N, N))
+        step = oracle.attempt_step(ocfg, params, 0.0, dt, 1.0, 1.0, m0, chol0)
+        np.testing.assert_array_equal(gpu["marg_mean"][0, 1].ravel(), step["mean"].ravel())
+        np.testing.assert_array_equal(gpu["marg_chol"][0, 1].reshape(N, N), step["chol"][0])
+        assert np.isfinite(step["error_norm"]) and step["dt_proposed"] > 0
