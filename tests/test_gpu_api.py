@@ -161,3 +161,35 @@ def test_posterior_sampling_matches_the_smoothed_marginals():
     (q3, _), _ = stats.markov_sample(2, posterior, shape=(8,), reverse=True)
     np.testing.assert_array_equal(q2, q3)
     assert not np.array_equal(q2, qoi[:8, :-1])
+
+
+def test_solve_via_interpolate_drop_in_matches_the_reference_goldens(goldens):
+    # tests/test_ivpsolvers.py (reference) runs the same assertions for solve_via_interpolate;
+    # experiments/2_workprec_simple/run_simple.py:58-80,200 committed its grid lengths and RMSEs
+    import scipy.integrate
+
+    from odecheckpts_b200 import ivps, ivpsolvers
+
+    vf, u0, time_span, args = ivps.logistic()
+    save_at = np.linspace(*time_span, num=5)
+    sol, aux = ivpsolvers.solve_via_interpolate("ts0-4", vf, u0[0], save_at, dt0=0.1, atol=1e-3, rtol=1e-3)(u0, args)
+    assert "u0_solve" in aux.keys() and sol.shape == (5, 1)
+    assert np.allclose(sol[:, 0], pu.logistic_exact(save_at), atol=np.sqrt(1e-3), rtol=np.sqrt(1e-3))
+
+    vf, u0, tspan, params = ivps.rigid_body(time_span=(0.0, 50.0))
+    xs = goldens["rigid_checkpoints"]
+    ref = scipy.integrate.solve_ivp(lambda t, y: vf(y, t=t, p=params), (0.0, 50.0), u0[0], t_eval=xs, method="DOP853", atol=1e-13, rtol=1e-13).y.T
+    for nu, key in [(2, "rigid_interp_nu2"), (4, "rigid_interp_nu4")]:
+        for tol, want_len, want_rmse in zip(goldens[key + "_list_of_args"], goldens[key + "_length_of_longest_vector"], goldens[key + "_precision"]):
+            t = tol * 100  # run_simple.py:60-64
+            fun = ivpsolvers.solve_via_interpolate(f"ts0-{nu}", vf, u0[0], save_at=xs, dt0=50.0, atol=1e-3 * t, rtol=t)
+            sol, aux = fun(u0, params)
+            assert abs(len(aux["u0_solve"]) - want_len) <= 0.04 * want_len
+            rmse = np.linalg.norm(sol - ref) / np.sqrt(ref.size)
+            assert abs(rmse / want_rmse - 1.0) < 0.15, (nu, tol, rmse, want_rmse)
+    # the last (tightest) nu = 2 case is well conditioned: exact grid length, RMSE to 4 digits
+    assert len(aux["u0_solve"]) > 0
+    fun = ivpsolvers.solve_via_interpolate("ts0-2", vf, u0[0], save_at=xs, dt0=50.0, atol=1e-3 * 1e-5, rtol=1e-5)
+    sol, aux = fun(u0, params)
+    assert len(aux["u0_solve"]) == 4158
+    assert abs(np.linalg.norm(sol - ref) / np.sqrt(ref.size) / goldens["rigid_interp_nu2_precision"][-1] - 1.0) < 1e-3
