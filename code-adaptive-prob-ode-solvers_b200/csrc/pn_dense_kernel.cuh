@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_kernel(const __grid_const
       for (int e = lane; e < Dn; e += 32) slot_base[e] = S_m[e];
       for (int e = lane; e < MAT; e += 32) slot_base[Dn + e] = 0.0;
     }
-    double t = a.save_at[0], dt_next = a.dt0, e_prev = 1.0;
+    double t = a.save_at[0], dt_next = a.dt0, e_prev = 1.0, le_prev = 0.0;
     double pend_t = 0.0, pend_sigma = 1.0;
     int mode = MODE_STEP;
     long long k_next = 1, n_acc = 0, n_rej = 0, n_att = 0;
@@ -470,12 +470,13 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_kernel(const __grid_const
         }
         e_norm = dsqrt(acc) * inv_sqrt_d;
       }
-      double fac;
+      double fac, le_now;
       {
-        const double ie = rcp(e_norm);
-        const double a1 = det_pow(ie, a.pow_i);
-        const double a2 = det_pow(e_prev * ie, a.pow_p);
-        fac = (a.safety * a1) * a2;
+        le_now = det_log(e_norm < 2.2250738585072014e-308 ? 2.2250738585072014e-308 : e_norm);
+        le_now = (e_norm == 0.0) ? -745.0 : le_now;
+        fac = a.safety * det_exp(fma(a.pow_p, le_prev, -((a.pow_i + a.pow_p) * le_now)));
+        fac = (e_norm == 0.0) ? a.factor_max : fac;
+        fac = (e_norm != e_norm) ? e_norm : fac;
         fac = (fac < a.factor_max) ? fac : a.factor_max;
         fac = (fac > a.factor_min) ? fac : a.factor_min;
       }
@@ -542,7 +543,10 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_kernel(const __grid_const
         } else {
           dt_next = fac * dt;
           if (e_norm <= 1.0 || fixed_grid) {
-            if (!fixed_grid) e_prev = e_norm;
+            if (!fixed_grid) {
+              e_prev = e_norm;
+              le_prev = le_now;
+            }
             n_acc += 1;
             const double t1 = fixed_grid ? t_ck : (t + dt);
             const bool overshoot = (k_next < a.K) && (t1 > t_ck + TIME_EPS);

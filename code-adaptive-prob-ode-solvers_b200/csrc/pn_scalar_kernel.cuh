@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
   // ---- per-lane persistent state --------------------------------------------------------
   bool have = false, exhausted = false;
   long long b = 0, vb = 0;
-  double t = 0.0, dt_next = 0.0, e_prev = 1.0, sigma_state = 1.0, sigma0 = 1.0;
+  double t = 0.0, dt_next = 0.0, e_prev = 1.0, le_prev = 0.0, sigma_state = 1.0, sigma0 = 1.0;
   double atol = a.atol, rtol = a.rtol;
   double par[P];
   int mode = MODE_STEP;
@@ -377,6 +377,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
         t = a.save_at[0];
         dt_next = a.dt0;
         e_prev = 1.0;
+        le_prev = 0.0;
         sigma_state = sigma0;
         mode = MODE_STEP;
         k_next = 1;
@@ -819,12 +820,14 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
       e_norm = dsqrt(acc) * inv_sqrt_d;
     }
     // PI controller
-    double fac;
+    double fac, le_now;
     {
-      double ie = rcp(e_norm);
-      double a1 = det_pow(ie, a.pow_i);
-      double a2 = det_pow(e_prev * ie, a.pow_p);
-      fac = (a.safety * a1) * a2;
+      // safety (1/e)^n1 (e_prev/e)^n2 = safety exp(n2 ln e_prev - (n1 + n2) ln e); ln e_prev is cached
+      le_now = det_log(e_norm < 2.2250738585072014e-308 ? 2.2250738585072014e-308 : e_norm);
+      le_now = (e_norm == 0.0) ? -745.0 : le_now;
+      fac = a.safety * det_exp(fma(a.pow_p, le_prev, -((a.pow_i + a.pow_p) * le_now)));
+      fac = (e_norm == 0.0) ? a.factor_max : fac;
+      fac = (e_norm != e_norm) ? e_norm : fac;
       fac = (fac < a.factor_max) ? fac : a.factor_max;
       fac = (fac > a.factor_min) ? fac : a.factor_min;
     }
@@ -1057,7 +1060,10 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
       } else {
         dt_next = fac * dt;
         if (e_norm <= 1.0 || fixed_grid) {
-          if (!fixed_grid) e_prev = e_norm;
+          if (!fixed_grid) {
+            e_prev = e_norm;
+            le_prev = le_now;
+          }
           n_acc += 1;
           const double t1 = fixed_grid ? t_ck : (t + dt);
           const bool overshoot = (k_next < a.K) && (t1 > t_ck + TIME_EPS);

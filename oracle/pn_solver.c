@@ -540,13 +540,25 @@ typedef struct {
 } pi_state;
 
 /* control_proportional_integral().apply  (App. A.3 last lines; ivpsolvers.py:52) */
+/* ln of an error norm as the controller uses it: subnormals are flushed, 0 maps to ln(DBL_TRUE_MIN) */
+static double pi_log(double e) {
+  if (e == 0.0) return -745.0;
+  return pn_det_log(e < 2.2250738585072014e-308 ? 2.2250738585072014e-308 : e);
+}
+
 static double pi_factor(const engine *E, double e, double e_prev) {
+  /* safety (1/e)^n1 (e_prev/e)^n2 = safety exp(n2 ln e_prev - (n1 + n2) ln e): one log and one exp per
+   * attempt (a GPU lane keeps ln e_prev from the step that was accepted) */
   double nn = (double)(E->nu + 1);
   double n1 = E->cfg.power_integral / nn, n2 = E->cfg.power_proportional / nn;
-  double ie = 1.0 / e;
-  double a1 = pn_det_pow(ie, n1);
-  double a2 = pn_det_pow(e_prev * ie, n2);
-  double fac = (E->cfg.safety * a1) * a2;
+  double fac;
+  if (e != e) {
+    fac = e;
+  } else if (e == 0.0) {
+    fac = E->cfg.factor_max;
+  } else {
+    fac = E->cfg.safety * pn_det_exp(fma(n2, pi_log(e_prev), -((n1 + n2) * pi_log(e))));
+  }
   fac = (fac < E->cfg.factor_max) ? fac : E->cfg.factor_max;
   fac = (fac > E->cfg.factor_min) ? fac : E->cfg.factor_min;
   return fac;
