@@ -23,7 +23,7 @@ NVCC_FLAGS = [
     # fp64 contract: no implicit contraction; every FMA in the kernels is an explicit fma()
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true",
     "-Xcompiler", "-fPIC",
-    "-diag-suppress", "177",
+    "-diag-suppress", "177,128",
 ]  # fmt: skip
 
 

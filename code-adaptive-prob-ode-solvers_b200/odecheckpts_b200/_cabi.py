@@ -207,26 +207,46 @@ def _chol_shape(desc):
     return (B, K, n, n)
 
 
+_PIN_MIN_BYTES = 1 << 20
+
+
+def _host_empty(shape, dtype=np.float64):
+    """Result buffer on the host.  Large results are page-locked (through torch's caching host
+    allocator, so repeated solves reuse the same pages): the device-to-host copy then runs at PCIe
+    speed instead of faulting in and staging fresh pageable memory on every call."""
+    nbytes = int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize
+    if nbytes >= _PIN_MIN_BYTES:
+        try:
+            import torch
+
+            if torch.cuda.is_available():
+                tdt = {np.dtype(np.float64): torch.float64, np.dtype(np.int64): torch.int64, np.dtype(np.int32): torch.int32}
+                return torch.empty(tuple(shape), dtype=tdt[np.dtype(dtype)], pin_memory=True).numpy()
+        except (ImportError, RuntimeError):
+            pass
+    return np.empty(shape, dtype=dtype)
+
+
 def solve_host(desc, u0, params, tol, save_at, output_scale0, *, full=False, device=0):
     """Host-buffer entry point (numpy in, numpy out)."""
     B, K, d, n = desc.batch, desc.num_save_at, desc.d, desc.nu + 1
     f64 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)  # noqa: E731
     u0, params, tol, save_at, output_scale0 = map(f64, (u0, params, tol, save_at, output_scale0))
     out = {
-        "u": np.empty((B, K, d)),
-        "u_std": np.empty((B, K, d)),
-        "n_accepted": np.empty((B, K), dtype=np.int64),
-        "n_rejected": np.empty(B, dtype=np.int64),
-        "status": np.empty(B, dtype=np.int32),
+        "u": _host_empty((B, K, d)),
+        "u_std": _host_empty((B, K, d)),
+        "n_accepted": _host_empty((B, K), np.int64),
+        "n_rejected": _host_empty((B,), np.int64),
+        "status": _host_empty((B,), np.int32),
     }
-    mm = np.empty((B, K, n, d)) if full else None
-    mc = np.empty(_chol_shape(desc)) if full else None
+    mm = _host_empty((B, K, n, d)) if full else None
+    mc = _host_empty(_chol_shape(desc)) if full else None
     rec = bool(desc.flags & FLAG_RECORD)
     cap = desc.traj_capacity
-    tt = np.empty((cap, B)) if rec else None
-    tu = np.empty((cap, d, B)) if rec else None
-    ts = np.empty((cap, B)) if rec else None
-    tl = np.empty(B, dtype=np.int64) if rec else None
+    tt = _host_empty((cap, B)) if rec else None
+    tu = _host_empty((cap, d, B)) if rec else None
+    ts = _host_empty((cap, B)) if rec else None
+    tl = _host_empty((B,), np.int64) if rec else None
     rc = lib().pn_b200_solve_save_at_host(
         C.byref(desc), _np_ptr(u0), _np_ptr(params), _np_ptr(tol), _np_ptr(save_at), _np_ptr(output_scale0),
         _np_ptr(out["u"]), _np_ptr(out["u_std"]), _np_ptr(mm), _np_ptr(mc),
