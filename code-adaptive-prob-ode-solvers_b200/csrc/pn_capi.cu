@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -101,8 +102,12 @@ static int resolve(const pn_b200_desc* d, const KernelEntry** out) {
   if (!k && d->correction == PN_B200_TS0 && d->factorisation == PN_B200_ISOTROPIC)
     k = find_kernel(FAMILY_GROUP_ISO, d->problem, d->nu, d->strategy, d->d);
   // warp-per-IVP dense family: dense factorisation with d > 1, EKF0 or EKF1
-  if (!k && d->factorisation == PN_B200_DENSE && d->d > 1)
-    k = find_kernel(FAMILY_DENSE, d->problem, d->nu, d->strategy, d->d);
+  if (!k && d->factorisation == PN_B200_DENSE && d->d > 1) {
+    // register-column kernel first (D <= 32); PN_B200_DENSE_SMEM=1 forces the shared-memory kernel (A/B runs)
+    const char* force = getenv("PN_B200_DENSE_SMEM");
+    if (!(force && force[0] == '1')) k = find_kernel(FAMILY_DENSE_ROWS, d->problem, d->nu, d->strategy, d->d);
+    if (!k) k = find_kernel(FAMILY_DENSE, d->problem, d->nu, d->strategy, d->d);
+  }
   // CTA-per-IVP wide family: isotropic EKF0 with a runtime dimension (Brusselator beyond the fixed sizes)
   if (!k && d->correction == PN_B200_TS0 && d->factorisation == PN_B200_ISOTROPIC && d->d >= 4 && d->d <= 4096 &&
       (d->d % 2) == 0)
@@ -125,7 +130,7 @@ static int resolve(const pn_b200_desc* d, const KernelEntry** out) {
 static int make_plan(const pn_b200_desc* d, Plan* p, bool need_device) {
   int rc = resolve(d, &p->k);
   if (rc) return rc;
-  p->smem = (p->k->family == FAMILY_DENSE)
+  p->smem = family_is_dense(p->k->family)
                 ? (size_t)p->k->smem_doubles * (p->k->threads / 32) * sizeof(double)  // per warp
                 : (size_t)p->k->smem_doubles * p->k->threads * sizeof(double);        // per thread
   if (p->k->family == FAMILY_WIDE) p->smem += ((size_t)2 * d->d + p->k->threads / 32 + 2) * sizeof(double);
@@ -400,7 +405,7 @@ int pn_b200_solve_save_at_host(const pn_b200_desc* desc, const double* u0, const
       {&d_std, nullptr, u_std, B * K * d * 8},
       {&d_mm, nullptr, marg_mean, marg_mean ? B * K * n * d * 8 : 0},
       {&d_mc, nullptr, marg_chol,
-       marg_chol ? B * K * (k->family == FAMILY_GROUP_BDIAG ? d : (k->family == FAMILY_DENSE ? d * d : 1)) * n * n * 8 : 0},
+       marg_chol ? B * K * (k->family == FAMILY_GROUP_BDIAG ? d : (family_is_dense(k->family) ? d * d : 1)) * n * n * 8 : 0},
       {&d_nacc, nullptr, n_accepted, B * K * 8},
       {&d_nrej, nullptr, n_rejected, B * 8},
       {&d_stat, nullptr, status, B * 4},

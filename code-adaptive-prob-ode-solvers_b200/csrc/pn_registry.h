@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include "pn_dense_kernel.cuh"
+#include "pn_dense_rows_kernel.cuh"
 #include "pn_sample_kernel.cuh"
 #include "pn_scalar_kernel.cuh"
 #include "pn_smooth_kernel.cuh"
@@ -14,8 +15,10 @@ enum : int {
   FAMILY_GROUP_ISO = 1,   // lane per dimension, identical factors (isotropic)
   FAMILY_GROUP_BDIAG = 2, // lane per dimension, per-dimension factors (blockdiag)
   FAMILY_DENSE = 3,       // warp per IVP, D x D factors in shared memory (dense, d > 1)
-  FAMILY_WIDE = 4         // CTA per IVP, isotropic, runtime dimension (Brusselator d = 2N up to 4096)
+  FAMILY_WIDE = 4,        // CTA per IVP, isotropic, runtime dimension (Brusselator d = 2N up to 4096)
+  FAMILY_DENSE_ROWS = 5   // 16 or 32 lanes per IVP, register-resident Householder columns (dense, D <= 32)
 };
+inline bool family_is_dense(int family) { return family == FAMILY_DENSE || family == FAMILY_DENSE_ROWS; }
 
 struct KernelEntry {
   int family, problem, nu, strategy;
@@ -119,6 +122,26 @@ struct DenseInstance {
   }
 };
 
+// dense factorisation with d > 1 and D <= 32: LANES lanes per IVP, columns in registers
+template <class Prob, int NU, int STRAT, int LANES, int WARPS>
+struct DenseRowsInstance {
+  using Lay = DenseLayout<NU + 1, Prob::D>;
+  using RL = DenseRowsLayout<NU + 1, Prob::D>;
+  static cudaError_t launch_solve(const SolveArgs& a, int grid, size_t smem, cudaStream_t s) {
+    pn_dense_rows_kernel<Prob, NU, STRAT, LANES, WARPS><<<grid, 32 * WARPS, smem, s>>>(a);
+    return cudaGetLastError();
+  }
+  static KernelEntry entry() {
+    KernelEntry e = DenseInstance<Prob, NU, STRAT, WARPS>::entry();  // same slots, same smoothing kernel
+    e.family = FAMILY_DENSE_ROWS;
+    e.group = LANES;
+    e.smem_doubles = (32 / LANES) * RL::SMEM_SLOT + RL::TABLES;  // per warp, see make_plan
+    e.solve_func = (const void*)&pn_dense_rows_kernel<Prob, NU, STRAT, LANES, WARPS>;
+    e.launch_solve = &launch_solve;
+    return e;
+  }
+};
+
 // isotropic problems with a large runtime dimension: CTA per IVP
 template <class Prob, int NU, int STRAT, int THREADS>
 struct WideInstance {
@@ -171,6 +194,8 @@ struct Registrar {
   static ::pn::Registrar PN_CAT(pn_reg_, __COUNTER__)(::pn::ScalarInstance<::pn::Prob, NU, STRAT, 1, 0, PN_SCALAR_THREADS>::entry())
 #define PN_REGISTER_DENSE(Prob, NU, STRAT, WARPS) \
   static ::pn::Registrar PN_CAT(pn_reg_, __COUNTER__)(::pn::DenseInstance<::pn::Prob, NU, STRAT, WARPS>::entry())
+#define PN_REGISTER_DENSE_ROWS(Prob, NU, STRAT, LANES, WARPS) \
+  static ::pn::Registrar PN_CAT(pn_reg_, __COUNTER__)(::pn::DenseRowsInstance<::pn::Prob, NU, STRAT, LANES, WARPS>::entry())
 #define PN_REGISTER_WIDE(Prob, NU, STRAT) \
   static ::pn::Registrar PN_CAT(pn_reg_, __COUNTER__)(::pn::WideInstance<::pn::Prob, NU, STRAT, 128>::entry())
 #define PN_REGISTER_SCALAR_T(Prob, NU, STRAT, THREADS) \
