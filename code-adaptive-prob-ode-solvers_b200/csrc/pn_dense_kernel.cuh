@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_kernel(const __grid_const
     if (lane == 0) tk = atomicAdd(a.ticket, 1ULL);
     tk = __shfl_sync(0xffffffffu, tk, 0);
     if (tk >= (unsigned long long)a.B) break;
-    const long long b = (long long)tk;
+    const long long b = a.order ? a.order[tk] : (long long)tk;
     double par[P];
 #pragma unroll
     for (int i = 0; i < P; ++i) par[i] = (i < a.num_params) ? a.params[b * a.num_params + i] : 0.0;

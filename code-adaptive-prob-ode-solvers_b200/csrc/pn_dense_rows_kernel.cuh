@@ -34,8 +34,8 @@ struct DenseRowsLayout {
   static constexpr int MAT = Dn * Dn;
   static constexpr int VB = 2 * Dn + 2;  // one reflector broadcast buffer
   static constexpr int TABLES = 2 * N * N;  // L_Q and the flipped Pascal matrix, once per CTA
-  // shared memory per IVP slot (doubles): 10 matrices + vectors, see the take() list in the kernel
-  static constexpr int SMEM_SLOT = 10 * MAT + 10 * Dn + 2 * DD * Dn + DD * DD + 2 * VB;
+  // shared memory per IVP slot (doubles): 7 matrices + vectors, see the take() list in the kernel
+  static constexpr int SMEM_SLOT = 7 * MAT + 9 * Dn + 2 * DD * Dn + DD * DD + 2 * VB;
 };
 
 template <class Prob, int NU, int STRAT, int LANES, int WARPS>
@@ -73,16 +73,19 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_rows_kernel(const __grid_
   // state
   double* S_m = take(Dn);   double* S_L = take(MAT);
   double* S_G = take(MAT);  double* S_g = take(Dn);  double* S_Lam = take(MAT);
-  // accepted-but-uncommitted state while a checkpoint is interpolated
-  double* P_m = take(Dn);   double* P_L = take(MAT);
-  // step outputs
+  // step outputs.  (m_new, L_new) is only written by an attempted step (MODE_STEP), so it doubles
+  // as the accepted-but-uncommitted state while the checkpoints inside that step are interpolated.
   double* m_ext = take(Dn); double* m_new = take(Dn);
   double* L_ext = take(MAT); double* L_new = take(MAT);
-  double* Gm = take(MAT);   double* gm = take(Dn);   double* Lm = take(MAT);
+  double* gm = take(Dn);
   // work
   double* m_p = take(Dn);   double* m_ext_p = take(Dn);
-  double* W1 = take(MAT);   // R11 of the block QR, then G of this step (rows)
-  double* W2 = take(MAT);   // R12 of the block QR, then Lam of this step (rows)
+  double* W1 = take(MAT);   // R11 of the block QR, then G of this step (rows), then the merged G
+  double* W2 = take(MAT);   // R12 of the block QR, then Lam of this step (rows), then the merged Lam
+  double* Gm = W1;
+  double* Lm = W2;
+  double* P_m = m_new;
+  double* P_L = L_new;
   double* gn_s = take(Dn);  double* dinv = take(Dn);
   double* H = take(d * Dn); double* HLs = take(d * Dn);
   double* Rs = take(d * d);
@@ -172,7 +175,7 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_rows_kernel(const __grid_
         drained = true;
       } else {
         have = true;
-        b = (long long)tk;
+        b = a.order ? a.order[tk] : (long long)tk;
 #pragma unroll
         for (int i = 0; i < P; ++i) par[i] = (i < a.num_params) ? a.params[b * a.num_params + i] : 0.0;
         atol = a.tol ? a.tol[2 * b] : a.atol;
@@ -437,6 +440,7 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_rows_kernel(const __grid_
             }
             gacc = fma(s, gn_s[l], gacc);
           }
+          __syncwarp();  // every lane is done with this step's G and Lam: W1 / W2 take the merged ones
           if (act) {
 #pragma unroll
             for (int j = 0; j < Dn; ++j) Gm[c * Dn + j] = accG[j];
@@ -567,7 +571,7 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_rows_kernel(const __grid_
         for (int i = j + 1; i < Dn; ++i) mc[i] = fma(-f, v[i], mc[i]);
         mc[j] = (c == j) ? R.beta : nj;
       }
-      if (act) {
+      if (act && mode == MODE_STEP) {
 #pragma unroll
         for (int j = 0; j < Dn; ++j) L_new[c * Dn + j] = (j <= c) ? mc[j] : 0.0;
         double acc = m_ext[c];
@@ -665,9 +669,7 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_rows_kernel(const __grid_
           const bool overshoot = (k_next < a.K) && (t1 > t_ck + TIME_EPS);
           if (overshoot) {
             pend_t = t1;
-            pend_sigma = sigma;
-            gcopy(P_m, m_new, Dn);
-            gcopy(P_L, L_new, MAT);
+            pend_sigma = sigma;  // the accepted state stays in (m_new, L_new) = (P_m, P_L)
             mode = MODE_INTERP_A;
           } else {
             t = t1;

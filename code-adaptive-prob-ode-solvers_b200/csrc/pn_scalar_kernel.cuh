@@ -67,6 +67,10 @@ struct SolveArgs {
   long long* n_rejected;  // [B]
   int32_t* status;        // [B]
   unsigned long long* ticket;
+  // nullable [B]: ticket -> member.  The host entry fills it (smallest tolerance first) when members
+  // carry their own tolerances, so the members with the most steps start first and the launch does
+  // not end on a tail of a few long solves.
+  const long long* order;
   // optional trajectory recording (solve_adaptive_save_every_step, vdp.py:77-79)
   double* traj_t;    // [cap][B]
   double* traj_u;    // [cap][D][B]
@@ -282,7 +286,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
         if (GROUP > 1) tk = __shfl_sync(gmask, tk, base);
       }
       if (tk < (unsigned long long)a.B) {
-        b = (long long)tk;
+        b = a.order ? a.order[tk] : (long long)tk;
         vb = WIDE ? 0 : (b * DV + ((GROUP > 1 && real) ? sub : 0));
         have = true;
         double u0[Q * DT];

@@ -44,7 +44,8 @@ def test_supported_and_workspace_queries_need_no_gpu():
     assert _cabi.supported(d)
     n, D, K, B = 5, 1, 5, 8
     slot = (n * n + n * D + n * (n + 1) // 2) + (n * D + n * (n + 1) // 2)
-    assert _cabi.workspace_bytes(d) == 256 + K * slot * B * 8  # [B][K][slot]
+    header = (256 + 2 * 128 * 4 + B * 8 + 255) // 256 * 256  # ticket + stats, ordering histogram / cursors, order[B]
+    assert _cabi.workspace_bytes(d) == header + K * slot * B * 8  # [B][K][slot]
     assert not _cabi.supported(_desc(_cabi, problem=3, d=14))  # Pleiades has no thread-per-IVP kernel
     assert not _cabi.supported(_desc(_cabi, factorisation=0))  # isotropic + ts1 is not a valid model
     assert not _cabi.supported(_desc(_cabi, nu=9))
