@@ -407,6 +407,42 @@ int pn_b200_markov_sample(const pn_b200_desc* desc, const void* workspace, size_
   return PN_B200_SUCCESS;
 }
 
+int pn_b200_log_marginal_likelihood(const pn_b200_desc* desc, const void* workspace, size_t workspace_bytes,
+                                    const int32_t* status, const double* data, const double* obs_std,
+                                    double* lml, void* cuda_stream) {
+  Plan p;
+  int rc = make_plan(desc, &p, false);
+  if (rc) return rc;
+  if (desc->strategy != PN_B200_FIXEDPOINT || !p.k->launch_lml)
+    return fail(PN_B200_ERR_UNSUPPORTED, "the log marginal likelihood needs a fixed-point solve of the thread-per-IVP or lane-per-dimension family");
+  if (!workspace || workspace_bytes < p.ws_ticket + p.ws_cond || !status || !data || !obs_std || !lml)
+    return fail(PN_B200_ERR_ARGUMENT, "bad likelihood arguments");
+  if (desc->batch == 0) return PN_B200_SUCCESS;
+  cudaStream_t stream = (cudaStream_t)cuda_stream;
+  LmlArgs a;
+  a.B = desc->batch;
+  a.K = desc->num_save_at;
+  a.dv = p.k->dv;
+  a.D = desc->d / p.k->dv;
+  a.per_dim = (p.k->family == FAMILY_GROUP_BDIAG) ? 1 : 0;
+  a.cond = (const double*)((const char*)workspace + p.ws_ticket);
+  a.status = status;
+  a.data = data;
+  a.obs_std = obs_std;
+  a.lml = lml;
+  // scratch: whitened residuals [B][K][d] + log|s| [B*dv][K], stream-ordered
+  const size_t nw = (size_t)desc->batch * desc->num_save_at * desc->d, nl = (size_t)desc->batch * p.k->dv * desc->num_save_at;
+  double* scratch = nullptr;
+  cudaError_t ce = cudaMallocAsync((void**)&scratch, (nw + nl) * sizeof(double), stream);
+  if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, std::string("cudaMallocAsync: ") + cudaGetErrorString(ce));
+  a.w = scratch;
+  a.logs = scratch + nw;
+  ce = p.k->launch_lml(a, stream);
+  cudaFreeAsync(scratch, stream);
+  if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, std::string("likelihood kernel launch: ") + cudaGetErrorString(ce));
+  return PN_B200_SUCCESS;
+}
+
 int pn_b200_set_profiling(int enable) {
   g_profiling = enable != 0;
   return PN_B200_SUCCESS;

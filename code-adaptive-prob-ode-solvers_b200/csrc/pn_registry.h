@@ -4,6 +4,7 @@
 
 #include "pn_dense_kernel.cuh"
 #include "pn_dense_rows_kernel.cuh"
+#include "pn_lml_kernel.cuh"
 #include "pn_sample_kernel.cuh"
 #include "pn_scalar_kernel.cuh"
 #include "pn_smooth_kernel.cuh"
@@ -33,6 +34,7 @@ struct KernelEntry {
   cudaError_t (*launch_solve)(const SolveArgs&, int grid, size_t smem, cudaStream_t);
   cudaError_t (*launch_smooth)(const SmoothArgs&, cudaStream_t);
   cudaError_t (*launch_sample)(const SampleArgs&, cudaStream_t);  // nullptr: family has no sampler yet
+  cudaError_t (*launch_lml)(const LmlArgs&, cudaStream_t);        // nullptr: no likelihood kernel for this family
 };
 
 void register_kernel(const KernelEntry& e);
@@ -56,10 +58,16 @@ struct ScalarInstance {
     pn_sample_kernel<NU + 1, DL><<<(unsigned)((total + 127) / 128), 128, 0, s>>>(a);
     return cudaGetLastError();
   }
+  static cudaError_t launch_lml(const LmlArgs& a, cudaStream_t s) {
+    pn_lml_sweep_kernel<NU + 1, DL><<<(unsigned)((a.B * a.dv + 127) / 128), 128, 0, s>>>(a);
+    pn_lml_reduce_kernel<0><<<(unsigned)((a.B + 127) / 128), 128, 0, s>>>(a);
+    return cudaGetLastError();
+  }
   static KernelEntry entry() {
     using Lay = Layout<NU + 1, DL>;
     KernelEntry e;
     e.launch_sample = (STRAT == 1) ? &launch_sample : nullptr;
+    e.launch_lml = (STRAT == 1) ? &launch_lml : nullptr;
     e.family = (GROUP == 1) ? FAMILY_SCALAR : (BDIAG ? FAMILY_GROUP_BDIAG : FAMILY_GROUP_ISO);
     e.group = GROUP;
     e.dv = DV;
@@ -101,6 +109,7 @@ struct DenseInstance {
   static KernelEntry entry() {
     KernelEntry e;
     e.launch_sample = nullptr;
+    e.launch_lml = nullptr;
     e.family = FAMILY_DENSE;
     e.group = 32;
     e.dv = 1;
@@ -160,6 +169,7 @@ struct WideInstance {
   static KernelEntry entry() {
     KernelEntry e;
     e.launch_sample = nullptr;
+    e.launch_lml = nullptr;
     e.family = FAMILY_WIDE;
     e.group = THREADS;
     e.dv = 1;

@@ -82,6 +82,7 @@ EXPORTS = (
     "pn_b200_get_kernel_info",
     "pn_b200_measure_fp64_peak",
     "pn_b200_markov_sample",
+    "pn_b200_log_marginal_likelihood",
     "pn_b200_set_profiling",
     "pn_b200_get_last_timing",
     "pn_b200_last_error",
@@ -186,6 +187,27 @@ def markov_sample_device(desc, workspace, status, seed, num_samples, stream=None
         rc = lib().pn_b200_markov_sample(
             C.byref(desc), C.c_void_p(workspace.data_ptr()), C.c_size_t(workspace.numel() * workspace.element_size()),
             C.c_void_p(status.data_ptr()), C.c_uint64(int(seed) & (2**64 - 1)), C.c_int64(int(num_samples)),
+            C.c_void_p(out.data_ptr()), C.c_void_p(s.cuda_stream),
+        )  # fmt: skip
+    check(rc)
+    return out
+
+
+def log_marginal_likelihood_device(desc, workspace, status, data, obs_std, stream=None):
+    """[B] log marginal likelihoods (torch CUDA tensor) of `data` [B, K, d] observed with noise `obs_std`
+    [B, K] at the checkpoints, from the conditionals a finished fixed-point solve left in `workspace`."""
+    import torch
+
+    dev = workspace.device
+    B, K, d = desc.batch, desc.num_save_at, desc.d
+    data = torch.as_tensor(data, dtype=torch.float64, device=dev).expand(B, K, d).contiguous()
+    obs_std = torch.as_tensor(obs_std, dtype=torch.float64, device=dev).expand(B, K).contiguous()
+    out = torch.empty((B,), dtype=torch.float64, device=dev)
+    s = torch.cuda.current_stream(dev) if stream is None else stream
+    with torch.cuda.device(dev):
+        rc = lib().pn_b200_log_marginal_likelihood(
+            C.byref(desc), C.c_void_p(workspace.data_ptr()), C.c_size_t(workspace.numel() * workspace.element_size()),
+            C.c_void_p(status.data_ptr()), C.c_void_p(data.data_ptr()), C.c_void_p(obs_std.data_ptr()),
             C.c_void_p(out.data_ptr()), C.c_void_p(s.cuda_stream),
         )  # fmt: skip
     check(rc)

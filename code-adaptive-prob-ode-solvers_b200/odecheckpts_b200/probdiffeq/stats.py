@@ -57,3 +57,31 @@ def markov_sample(key, markov_seq, *, shape, reverse):
     if not batched:
         out = out[0]
     return (out[..., :-1, :], None), (out[..., -1, :], None)
+
+
+def log_marginal_likelihood(u, /, *, standard_deviation, posterior):
+    """Log marginal likelihood of observations `u` [K, d] of the ODE solution at the checkpoints, observed
+    with noise `standard_deviation` [K] (src/odecheckpts/train_util.py:22-24; forward value only -- the
+    reference differentiates it with jax, which is out of scope here).  Ensembles: `u` may be [B, K, d]
+    and `standard_deviation` [B, K]; the result is then [B].  Needs ``keep_conditionals=True``.
+
+    Like probdiffeq's reverse Kalman-filter estimator this is the running MEAN over the K data points of
+    log p(u_k | u_{k+1}, ..., u_{K-1}), i.e. the joint log density divided by K."""
+    if not isinstance(posterior, MarkovSeq):
+        raise TypeError("expected the .posterior of a solve_adaptive_save_at solution")
+    if posterior.handle is None:
+        raise ValueError("the solution did not keep its backward conditionals: pass keep_conditionals=True to the solve")
+    import numpy as np
+
+    from .. import _cabi
+
+    desc, workspace, status, as_numpy, batched = posterior.handle
+    K = desc.num_save_at
+    if np.ndim(u) < 2:
+        raise ValueError("u must have shape (K, d) (or (B, K, d) for an ensemble)")
+    if tuple(np.shape(standard_deviation))[-1:] != (K,) or tuple(np.shape(u))[-2] != K:
+        raise ValueError("u and standard_deviation need one entry per checkpoint")
+    out = _cabi.log_marginal_likelihood_device(desc, workspace, status, u, standard_deviation)
+    if as_numpy:
+        out = out.cpu().numpy()
+    return out if batched else out[0]

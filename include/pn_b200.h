@@ -119,6 +119,20 @@ int pn_b200_markov_sample(const pn_b200_desc* desc, const void* workspace, size_
                           const int32_t* status, uint64_t seed, int64_t num_samples, double* samples,
                           void* cuda_stream);
 
+/*
+ * Log marginal likelihood of observations of the ODE solution at the checkpoints, from a FINISHED
+ * fixed-point solve: stats.log_marginal_likelihood(u, standard_deviation=, posterior=),
+ * src/odecheckpts/train_util.py:22-24 (the parameter-inference loss, forward value only).
+ * `workspace` / `status` are the buffers the solve call used.  data: [B][K][d] observed values of u
+ * at save_at[0..K-1]; obs_std: [B][K] observation noise standard deviations (> 0); lml: [B] (all
+ * DEVICE pointers).  lml[b] is the running mean over the K data points of
+ * log p(y_k | y_{k+1}, ..., y_{K-1}) -- probdiffeq's reverse Kalman-filter estimator -- i.e. the joint
+ * log density divided by K; NaN for failed members.  Thread-per-IVP and lane-per-dimension families.
+ */
+int pn_b200_log_marginal_likelihood(const pn_b200_desc* desc, const void* workspace, size_t workspace_bytes,
+                                    const int32_t* status, const double* data, const double* obs_std,
+                                    double* lml, void* cuda_stream);
+
 /* Launch geometry and compiled resource usage of the kernel that serves `desc` (for reports). */
 typedef struct {
   int32_t threads_per_cta, ctas_per_sm, num_sms, grid;

@@ -134,6 +134,19 @@ int pn_oracle_solve_save_at(const pn_oracle_config *cfg, const double *u0, const
                             int64_t *n_accepted, int64_t *n_rejected, int32_t *status,
                             double *filt_u);
 
+/* The same solve plus stats.log_marginal_likelihood of observations at the checkpoints
+ * (src/odecheckpts/train_util.py:22-24): data [K,d], obs_std [K]; *lml = running mean over the K
+ * data points of log p(y_k | y_{k+1..K-1}) (probdiffeq's reverse Kalman filter estimator), NaN for the
+ * filter strategy and for dense with d > 1.  Optional: cond_out [K, F*N*N + N*Ctot + F*N*N] the
+ * backward conditionals (G, g, Lam) checkpoint k -> k-1, scale_out [K,F] the output scale carried by
+ * each checkpoint.  PARITY UNPINNED: probdiffeq's sources are absent and the reference commits no
+ * likelihood values; tests check it against a brute-force joint Gaussian instead. */
+int pn_oracle_solve_save_at_lml(const pn_oracle_config *cfg, const double *u0, const double *params,
+                                const double *save_at, int64_t K, double output_scale0,
+                                const double *data, const double *obs_std, double *u, double *u_std,
+                                double *marg_mean, double *marg_chol, double *cond_out,
+                                double *scale_out, double *lml, int32_t *status);
+
 /* Ensemble: members are independent; OpenMP over members (num_threads<=0: all cores).
  * u0: [B,q,d]; params: [B,P]; tol: nullable [B,2] per-member (atol, rtol);
  * outputs member-major: u [B,K,d], u_std [B,K,d], n_accepted [B,K], n_rejected [B], status [B]. */

@@ -259,6 +259,39 @@ def solve_save_at(cfg, u0, params, save_at, output_scale0=1.0, full=False):
     return out
 
 
+def solve_save_at_lml(cfg, u0, params, save_at, data, obs_std, output_scale0=1.0):
+    """Checkpoint solve + stats.log_marginal_likelihood(data, standard_deviation=obs_std, posterior=...)
+    (train_util.py:22-24).  Also returns the backward conditionals and per-checkpoint output scales."""
+    u0 = _f64(u0)
+    save_at = _f64(save_at)
+    K = len(save_at)
+    d = cfg.d
+    F, N, Ct = _engine_dims(cfg)
+    p = _f64(params if len(params) else [0.0])
+    data = _f64(np.asarray(data, dtype=float).reshape(K, d))
+    obs_std = _f64(np.broadcast_to(np.asarray(obs_std, dtype=float), (K,)))
+    u, u_std = np.zeros((K, d)), np.zeros((K, d))
+    mm, mc = np.zeros((K, N, Ct)), np.zeros((K, F, N, N))
+    cond = np.zeros((K, 2 * F * N * N + N * Ct))
+    scale = np.zeros((K, F))
+    lml = C.c_double(0.0)
+    status = C.c_int32(0)
+    rc = lib().pn_oracle_solve_save_at_lml(
+        C.byref(cfg), _dptr(u0), _dptr(p), _dptr(save_at), C.c_int64(K), C.c_double(output_scale0),
+        _dptr(data), _dptr(obs_std), _dptr(u), _dptr(u_std), _dptr(mm), _dptr(mc), _dptr(cond), _dptr(scale),
+        C.byref(lml), C.byref(status),
+    )  # fmt: skip
+    if rc:
+        raise ValueError(f"oracle rejected the configuration (rc={rc})")
+    FNN = F * N * N
+    return {
+        "u": u, "u_std": u_std, "marg_mean": mm, "marg_chol": mc, "status": int(status.value), "lml": float(lml.value),
+        "output_scale": scale,
+        "cond_G": cond[:, :FNN].reshape(K, F, N, N), "cond_g": cond[:, FNN:FNN + N * Ct].reshape(K, N, Ct),
+        "cond_Lam": cond[:, FNN + N * Ct:].reshape(K, F, N, N),
+    }  # fmt: skip
+
+
 def solve_save_at_batch(cfg, u0, params, save_at, tol=None, output_scale0=None, num_threads=0):
     """u0: (B, q, d); params: (B, P)."""
     u0 = _f64(u0)

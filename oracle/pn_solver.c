@@ -753,11 +753,76 @@ int pn_oracle_attempt_step(const pn_oracle_config *cfg, const double *params, do
 /* ------------------------------------------------------------------------- */
 /* public: solve_adaptive_save_at + backward marginalisation                  */
 /* ------------------------------------------------------------------------- */
+/* optional outputs of the checkpoint solver beyond (u, u_std, marginals) */
+typedef struct {
+  const double *lml_data; /* [K,d] observations of u at the checkpoints              */
+  const double *lml_std;  /* [K] observation noise standard deviations               */
+  double *lml_out;        /* scalar                                                  */
+  double *cond_out;       /* nullable [K, F*N*N + N*Ctot + F*N*N]: (G, g, Lam) of the
+                             conditional checkpoint k -> k-1 (entry 0 unused)         */
+  double *scale_out;      /* nullable [K, F] output scale carried by each checkpoint  */
+} solve_extras;
+
+/* stats.log_marginal_likelihood(u, standard_deviation=, posterior=) (src/odecheckpts/train_util.py:22-24,
+ * experiments/old/6_learn_ode/learn.py:112-114): a Kalman filter that runs BACKWARDS over the
+ * checkpoint Markov sequence.  Start from the terminal marginal; at checkpoint k observe
+ * y_k = (0-th derivative) + N(0, std_k^2) in square-root form (QR of [[std, 0], [L^T e_0, L^T]]),
+ * add log N(y_k; m_0, s^2) to a RUNNING MEAN over the data points (probdiffeq's estimator keeps
+ * (rv, num_data, mean logpdf)), condition on y_k, and move to checkpoint k-1 through the stored
+ * backward conditional.  Kronecker factorisations and dense with d == 1. */
+#define PN_HALF_LOG_2PI 0.91893853320467274178
+static double lml_sweep(engine *E, pstate *emit, int64_t K, const double *data, const double *std) {
+  int N = E->N, Ct = E->Ctot, C = E->C, d = E->d, M1 = E->N + 1;
+  size_t NN = (size_t)N * N;
+  if (E->dense) return NAN;
+  pstate rv, nxt;
+  pstate_alloc(E, &rv);
+  pstate_alloc(E, &nxt);
+  pstate_copy(E, &rv, &emit[K - 1]);
+  double *M = E->M2; /* (N+1)^2 <= 4 N^2 */
+  double mean_lp = 0.0, ndata = 0.0;
+  for (int64_t k = K - 1; k >= 0; --k) {
+    double lp = 0.0;
+    for (int f = 0; f < E->F; ++f) {
+      double *L = rv.chol + f * NN;
+      for (int j = 0; j < M1 * M1; ++j) M[j] = 0.0;
+      M[0] = std[k];
+      for (int i = 0; i < N; ++i) {
+        M[(1 + i) * M1] = L[i]; /* (L^T e_0)_i = L[0][i] */
+        for (int j = 0; j < N; ++j) M[(1 + i) * M1 + 1 + j] = L[j * N + i];
+      }
+      pn_qr_r(M, M1, M1);
+      double s = M[0], inv_s = 1.0 / s;
+      double log_s = pn_det_log(fabs(s));
+      for (int c = f * C; c < f * C + C; ++c) {
+        double z = rv.mean[c] - data[k * d + c];
+        double w = z * inv_s;
+        lp = fma(-0.5 * w, w, lp);
+        for (int i = 0; i < N; ++i) {
+          double gi = M[1 + i] * inv_s;
+          rv.mean[i * Ct + c] = fma(-gi, z, rv.mean[i * Ct + c]);
+        }
+      }
+      lp = fma(-(double)C, log_s + PN_HALF_LOG_2PI, lp);
+      for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) L[i * N + j] = (j <= i) ? M[(1 + j) * M1 + 1 + i] : 0.0;
+    }
+    mean_lp = fma(mean_lp, ndata, lp) * (1.0 / (ndata + 1.0));
+    ndata += 1.0;
+    if (k == 0) break;
+    marginalise(E, &rv, &emit[k], &nxt);
+    pstate t2 = rv; rv = nxt; nxt = t2;
+  }
+  pstate_free(&rv);
+  pstate_free(&nxt);
+  return mean_lp;
+}
+
 static int solve_save_at_impl(engine *E, const double *u0, const double *params,
                               const double *save_at, int64_t K, double output_scale0, double atol,
                               double rtol, double *u, double *u_std, double *marg_mean,
                               double *marg_chol, int64_t *n_accepted, int64_t *n_rejected,
-                              int32_t *status, double *filt_u) {
+                              int32_t *status, double *filt_u, const solve_extras *X) {
   int N = E->N, Ct = E->Ctot, d = E->d;
   size_t NN = (size_t)N * N, NC = (size_t)N * Ct, FNN = (size_t)E->F * NN;
   int fixedpoint = (E->cfg.strategy == PN_STRATEGY_FIXEDPOINT);
@@ -847,7 +912,19 @@ static int solve_save_at_impl(engine *E, const double *u0, const double *params,
     }
     pstate_free(&rv);
     pstate_free(&rv_prev);
+    if (X && X->cond_out) {
+      size_t stride = 2 * FNN + NC;
+      for (int64_t k = 0; k < K; ++k) {
+        memcpy(X->cond_out + k * stride, emit[k].G, sizeof(double) * FNN);
+        memcpy(X->cond_out + k * stride + FNN, emit[k].g, sizeof(double) * NC);
+        memcpy(X->cond_out + k * stride + FNN + NC, emit[k].Lam, sizeof(double) * FNN);
+      }
+    }
+    if (X && X->scale_out)
+      for (int64_t k = 0; k < K; ++k) memcpy(X->scale_out + k * E->F, emit[k].sigma, sizeof(double) * E->F);
+    if (X && X->lml_out) *X->lml_out = fixedpoint ? lml_sweep(E, emit, K, X->lml_data, X->lml_std) : NAN;
   } else {
+    if (X && X->lml_out) *X->lml_out = NAN;
     for (int64_t k = 0; k < K * d; ++k) { u[k] = NAN; u_std[k] = NAN; }
     if (n_accepted) for (int64_t k = k_done + 1; k < K; ++k) n_accepted[k] = A.n_accepted;
   }
@@ -870,7 +947,22 @@ int pn_oracle_solve_save_at(const pn_oracle_config *cfg, const double *u0, const
   int rc = engine_init(&E, cfg);
   if (rc) return rc;
   rc = solve_save_at_impl(&E, u0, params, save_at, K, output_scale0, cfg->atol, cfg->rtol, u, u_std,
-                          marg_mean, marg_chol, n_accepted, n_rejected, status, filt_u);
+                          marg_mean, marg_chol, n_accepted, n_rejected, status, filt_u, NULL);
+  engine_free(&E);
+  return rc;
+}
+
+int pn_oracle_solve_save_at_lml(const pn_oracle_config *cfg, const double *u0, const double *params,
+                                const double *save_at, int64_t K, double output_scale0,
+                                const double *data, const double *obs_std, double *u, double *u_std,
+                                double *marg_mean, double *marg_chol, double *cond_out,
+                                double *scale_out, double *lml, int32_t *status) {
+  engine E;
+  int rc = engine_init(&E, cfg);
+  if (rc) return rc;
+  solve_extras X = {data, obs_std, lml, cond_out, scale_out};
+  rc = solve_save_at_impl(&E, u0, params, save_at, K, output_scale0, cfg->atol, cfg->rtol, u, u_std,
+                          marg_mean, marg_chol, NULL, NULL, status, NULL, &X);
   engine_free(&E);
   return rc;
 }
@@ -901,7 +993,7 @@ int pn_oracle_solve_save_at_batch(const pn_oracle_config *cfg, int64_t B, const 
         double os0 = output_scale0 ? output_scale0[b] : 1.0;
         solve_save_at_impl(&E, u0 + (size_t)b * q * d, params + (size_t)b * P, save_at, K, os0, atol,
                            rtol, u + (size_t)b * K * d, u_std + (size_t)b * K * d, NULL, NULL,
-                           n_accepted + (size_t)b * K, n_rejected + b, status + b, NULL);
+                           n_accepted + (size_t)b * K, n_rejected + b, status + b, NULL, NULL);
       }
       engine_free(&E);
     }
