@@ -281,7 +281,8 @@ def main():
     pin[1].copy_(torch.from_numpy(u0_h[:, 1, :]))
     u0_pin = (pin[0].numpy(), pin[1].numpy())
     e2e_steps = max(2, min(args.steps, 3))
-    solve(u0_pin, ())  # warm-up
+    res, aux = solve(u0_pin, ())  # warm-up: two calls, so that both generations of recycled host result
+    res, aux = solve(u0_pin, ())  # buffers exist (the previous results are still alive during a call)
     barrier()
     t_e2e = time.perf_counter()
     for _ in range(e2e_steps):

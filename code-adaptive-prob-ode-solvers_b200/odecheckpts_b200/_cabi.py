@@ -229,10 +229,58 @@ def _chol_shape(desc):
     return (B, K, n, n)
 
 
+class _HostPool:
+    """Recycled page-locked result buffers for the host entry point.
+
+    Fresh pageable arrays cost a page fault per 4 KB while the device-to-host copy fills them, and
+    page-locking a fresh buffer on every call costs more than it saves.  So large result buffers are
+    page-locked ONCE (torch's pinned allocator) and come back here when the numpy array handed to the
+    caller -- and every view of it -- has been garbage collected; the next solve of the same size takes
+    them again.  Capped; anything beyond the cap is simply freed."""
+
+    MIN_BYTES = 1 << 20
+    MAX_POOLED_BYTES = 2 << 30
+
+    def __init__(self):
+        self.free = {}
+        self.pooled = 0
+
+    def take(self, shape, dtype):
+        import weakref
+
+        import torch
+
+        nbytes = int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize
+        blocks = self.free.get(nbytes)
+        if blocks:
+            block = blocks.pop()
+            self.pooled -= nbytes
+        else:
+            block = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        base = block.numpy()
+        weakref.finalize(base, self._give_back, block, nbytes)
+        return base.view(dtype).reshape(shape)
+
+    def _give_back(self, block, nbytes):
+        if self.pooled + nbytes <= self.MAX_POOLED_BYTES:
+            self.free.setdefault(nbytes, []).append(block)
+            self.pooled += nbytes
+
+
+_host_pool = _HostPool()
+
+
 def _host_empty(shape, dtype=np.float64):
-    """Result buffer on the host.  Plain pageable memory: page-locking fresh result buffers on every
-    call (measured on the headline workload, 79 MB of results) costs more than the faster copy saves,
-    because the previous call's results are normally still alive and nothing can be reused."""
+    """Result buffer on the host: recycled page-locked memory for large results, plain numpy otherwise."""
+    nbytes = int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize
+    if nbytes >= _HostPool.MIN_BYTES:
+        try:
+            import torch
+
+            if torch.cuda.is_available():
+                return _host_pool.take(shape, dtype)
+        except (ImportError, RuntimeError):
+            pass
     return np.empty(shape, dtype=dtype)
 
 

@@ -1,6 +1,6 @@
 """Throughput of the other BASELINE configs (parity-test cases, not the bench line): SURVEY 8d C3/C4/C5.
 
-    python scripts/config_throughput.py [--big]            # on a B200
+    python scripts/config_throughput.py [--big] [--only SUBSTRING]      # on a B200
 """
 import json
 import os
@@ -20,7 +20,12 @@ def T(x):
     return torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float64, device=dev)
 
 
+ONLY = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None
+
+
 def run(name, desc, u0, params, tol, save_at, reps=3):
+    if ONLY is not None and ONLY not in name:
+        return
     args = (T(u0), None if params is None else T(params), None if tol is None else T(tol), T(save_at), None)
     out = None
     best = 1e30
