@@ -280,7 +280,7 @@ int pn_b200_get_kernel_info(const pn_b200_desc* desc, pn_b200_kernel_info* info)
 int pn_b200_solve_save_at(const pn_b200_desc* desc, const double* u0, const double* params,
                           const double* tol, const double* save_at, const double* output_scale0,
                           double* u, double* u_std, double* marg_mean, double* marg_chol,
-                          int64_t* n_accepted, int64_t* n_rejected, int32_t* status, double* traj_t,
+                          double* output_scale, int64_t* n_accepted, int64_t* n_rejected, int32_t* status, double* traj_t,
                           double* traj_u, double* traj_std, int64_t* traj_len, void* workspace,
                           size_t workspace_bytes, void* cuda_stream) {
   Plan p;
@@ -322,6 +322,7 @@ int pn_b200_solve_save_at(const pn_b200_desc* desc, const double* u0, const doub
   a.cond = (double*)((char*)workspace + p.ws_ticket);
   a.wide_d = (p.k->family == FAMILY_WIDE) ? desc->d : 0;
   a.wide_mean = (double*)((char*)workspace + p.ws_ticket + p.ws_cond);
+  a.out_scale = output_scale;
   a.n_accepted = (long long*)n_accepted;
   a.n_rejected = (long long*)n_rejected;
   a.status = status;
@@ -460,7 +461,7 @@ int pn_b200_get_last_timing(float* solve_ms, float* smooth_ms) {
 int pn_b200_solve_save_at_host(const pn_b200_desc* desc, const double* u0, const double* params,
                                const double* tol, const double* save_at, const double* output_scale0,
                                double* u, double* u_std, double* marg_mean, double* marg_chol,
-                               int64_t* n_accepted, int64_t* n_rejected, int32_t* status, double* traj_t,
+                               double* output_scale, int64_t* n_accepted, int64_t* n_rejected, int32_t* status, double* traj_t,
                                double* traj_u, double* traj_std, int64_t* traj_len, int device) {
   cudaError_t ce = cudaSetDevice(device);
   if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, cudaGetErrorString(ce));
@@ -479,6 +480,7 @@ int pn_b200_solve_save_at_host(const pn_b200_desc* desc, const double* u0, const
     size_t bytes;
   };
   void *d_u0 = 0, *d_par = 0, *d_tol = 0, *d_save = 0, *d_os = 0, *d_u = 0, *d_std = 0, *d_mm = 0, *d_mc = 0;
+  void* d_sc = 0;
   void *d_nacc = 0, *d_nrej = 0, *d_stat = 0, *d_tt = 0, *d_tu = 0, *d_ts = 0, *d_tl = 0, *d_ws = 0;
   size_t ws_bytes = pn_b200_workspace_bytes(desc);
   Buf bufs[] = {
@@ -492,6 +494,7 @@ int pn_b200_solve_save_at_host(const pn_b200_desc* desc, const double* u0, const
       {&d_mm, nullptr, marg_mean, marg_mean ? B * K * n * d * 8 : 0},
       {&d_mc, nullptr, marg_chol,
        marg_chol ? B * K * (k->family == FAMILY_GROUP_BDIAG ? d : (family_is_dense(k->family) ? d * d : 1)) * n * n * 8 : 0},
+      {&d_sc, nullptr, output_scale, output_scale ? B * K * (k->family == FAMILY_GROUP_BDIAG ? d : 1) * 8 : 0},
       {&d_nacc, nullptr, n_accepted, B * K * 8},
       {&d_nrej, nullptr, n_rejected, B * 8},
       {&d_stat, nullptr, status, B * 4},
@@ -526,7 +529,7 @@ int pn_b200_solve_save_at_host(const pn_b200_desc* desc, const double* u0, const
   if (rc == PN_B200_SUCCESS)
     rc = pn_b200_solve_save_at(desc, (const double*)d_u0, (const double*)d_par, (const double*)d_tol,
                                (const double*)d_save, (const double*)d_os, (double*)d_u, (double*)d_std,
-                               (double*)d_mm, (double*)d_mc, (int64_t*)d_nacc, (int64_t*)d_nrej,
+                               (double*)d_mm, (double*)d_mc, (double*)d_sc, (int64_t*)d_nacc, (int64_t*)d_nrej,
                                (int32_t*)d_stat, (double*)d_tt, (double*)d_tu, (double*)d_ts, (int64_t*)d_tl,
                                d_ws, ws_bytes, stream);
   if (rc == PN_B200_SUCCESS) {

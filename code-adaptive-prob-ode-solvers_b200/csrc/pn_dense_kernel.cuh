@@ -223,10 +223,11 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_kernel(const __grid_const
       for (int e = lane; e < MAT; e += 32) slot_base[Dn + e] = 0.0;
     }
     double t = a.save_at[0], dt_next = a.dt0, e_prev = 1.0, le_prev = 0.0;
-    double pend_t = 0.0, pend_sigma = 1.0;
+    double pend_t = 0.0, pend_sigma = 1.0, sigma_state = sigma0;
     int mode = MODE_STEP;
     long long k_next = 1, n_acc = 0, n_rej = 0, n_att = 0;
     if (lane == 0) a.n_accepted[b * a.K] = 0;
+    if (lane == 0 && a.out_scale) a.out_scale[b * a.K] = sigma0;
     bool finished = false;
     int st = 0;
 
@@ -514,6 +515,7 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_kernel(const __grid_const
             emit_marg(slot, S_m, S_L);
           }
           if (lane == 0) a.n_accepted[b * a.K + k_next] = n_acc;
+          if (lane == 0 && a.out_scale) a.out_scale[b * a.K + k_next] = sigma_state;
           k_next += 1;
         }
         if (k_next >= a.K) finished = true;
@@ -523,6 +525,7 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_kernel(const __grid_const
           mode = MODE_INTERP_A;
         } else {
           t = pend_t;
+          sigma_state = pend_sigma;
           wc::copy(S_m, P_m, Dn, lane);
           wc::copy(S_L, P_L, MAT, lane);
           if (FIX) {
@@ -558,6 +561,7 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_kernel(const __grid_const
               mode = MODE_INTERP_A;
             } else {
               t = t1;
+              sigma_state = sigma;
               wc::copy(S_m, m_new, Dn, lane);
               wc::copy(S_L, L_new, MAT, lane);
               if (FIX) {
@@ -588,6 +592,7 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_kernel(const __grid_const
         wc::copy(S_m, m_ext, Dn, lane);
         wc::copy(S_L, L_ext, MAT, lane);
         if (lane == 0) a.n_accepted[b * a.K + k_next] = n_acc;
+        if (lane == 0 && a.out_scale) a.out_scale[b * a.K + k_next] = pend_sigma;
         if (FIX) {
           mode = MODE_INTERP_B;
         } else {

@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_rows_kernel(const __grid_
   double par[P];
   double atol = 0.0, rtol = 0.0, sigma0 = 1.0;
   double* slot_base = nullptr;
-  double t = 0.0, dt_next = 0.0, le_prev = 0.0, pend_t = 0.0, pend_sigma = 1.0;
+  double t = 0.0, dt_next = 0.0, le_prev = 0.0, pend_t = 0.0, pend_sigma = 1.0, sigma_state = 1.0;
   int mode = MODE_STEP, st = 0;
   long long k_next = 1, n_acc = 0, n_rej = 0, n_att = 0;
 #pragma unroll
@@ -206,11 +206,13 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_rows_kernel(const __grid_
         le_prev = 0.0;
         pend_t = 0.0;
         pend_sigma = 1.0;
+        sigma_state = sigma0;
         mode = MODE_STEP;
         k_next = 1;
         n_acc = n_rej = n_att = 0;
         st = 0;
         if (c == 0) a.n_accepted[b * a.K] = 0;
+        if (c == 0 && a.out_scale) a.out_scale[b * a.K] = sigma0;
       }
     }
     if (__all_sync(0xffffffffu, !have)) break;
@@ -634,6 +636,7 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_rows_kernel(const __grid_
           emit_marg(slot, S_m, S_L);
         }
         if (c == 0) a.n_accepted[b * a.K + k_next] = n_acc;
+        if (c == 0 && a.out_scale) a.out_scale[b * a.K + k_next] = sigma_state;
         k_next += 1;
       }
       if (k_next >= a.K) finished = true;
@@ -643,6 +646,7 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_rows_kernel(const __grid_
         mode = MODE_INTERP_A;
       } else {
         t = pend_t;
+        sigma_state = pend_sigma;
         gcopy(S_m, P_m, Dn);
         gcopy(S_L, P_L, MAT);
         if (FIX) {
@@ -673,6 +677,7 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_rows_kernel(const __grid_
             mode = MODE_INTERP_A;
           } else {
             t = t1;
+            sigma_state = sigma;
             gcopy(S_m, m_new, Dn);
             gcopy(S_L, L_new, MAT);
             if (FIX) {
@@ -703,6 +708,7 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_rows_kernel(const __grid_
       gcopy(S_m, m_ext, Dn);
       gcopy(S_L, L_ext, MAT);
       if (c == 0) a.n_accepted[b * a.K + k_next] = n_acc;
+      if (c == 0 && a.out_scale) a.out_scale[b * a.K + k_next] = pend_sigma;
       if (FIX) {
         mode = MODE_INTERP_B;
       } else {

@@ -71,6 +71,9 @@ struct SolveArgs {
   // carry their own tolerances, so the members with the most steps start first and the launch does
   // not end on a tail of a few long solves.
   const long long* order;
+  // nullable [B][K][S]: the output scale carried by every checkpoint (solution.output_scale);
+  // S = d for the blockdiag factorisation (one scale per dimension), else 1
+  double* out_scale;
   // optional trajectory recording (solve_adaptive_save_every_step, vdp.py:77-79)
   double* traj_t;    // [cap][B]
   double* traj_u;    // [cap][D][B]
@@ -271,6 +274,17 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
   unsigned long long stat_warp_iters = 0, stat_lane_iters = 0, stat_interp_iters = 0;
   const long long clk0 = clock64();
 
+  // solution.output_scale at checkpoint k: one value per IVP, one per dimension for blockdiag
+  auto emit_scale = [&](long long k, double v) {
+    if (a.out_scale) {
+      if (BDIAG) {
+        if (real) a.out_scale[(b * a.K + k) * DT + sub] = v;
+      } else if (leader) {
+        a.out_scale[b * a.K + k] = v;
+      }
+    }
+  };
+
   for (;;) {
     // ---- fetch a member ----------------------------------------------------------------
     if (!have && !exhausted) {
@@ -387,6 +401,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
         k_next = 1;
         n_acc = n_rej = n_att = 0;
         if (leader) a.n_accepted[b * a.K] = 0;
+        emit_scale(0, sigma0);
         if (GROUP == 1 && (a.flags & FLAG_RECORD)) {
           a.traj_t[b] = t;
 #pragma unroll
@@ -1029,6 +1044,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
           store_state(slot);
         }
         if (leader) a.n_accepted[b * a.K + k_next] = n_acc;
+        emit_scale(k_next, sigma_state);
         k_next += 1;
       }
       if (k_next >= a.K) fin = true;
@@ -1138,6 +1154,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
         for (int j = 0; j <= i; ++j) SL(i, j) = L_ext[i][j];
       }
       if (leader) a.n_accepted[b * a.K + k_next] = n_acc;
+      emit_scale(k_next, sigma_given);
       if (FIX) {
         mode = MODE_INTERP_B;
       } else {

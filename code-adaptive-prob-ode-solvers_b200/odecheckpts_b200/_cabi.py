@@ -111,15 +111,17 @@ def lib():
         L.pn_b200_workspace_bytes.restype = C.c_size_t
         L.pn_b200_workspace_bytes.argtypes = [C.POINTER(Desc)]
         L.pn_b200_solve_save_at.restype = C.c_int
-        L.pn_b200_solve_save_at.argtypes = [C.POINTER(Desc)] + [dp] * 16 + [vp, C.c_size_t, vp]
+        L.pn_b200_solve_save_at.argtypes = [C.POINTER(Desc)] + [dp] * 17 + [vp, C.c_size_t, vp]
         L.pn_b200_solve_save_at_host.restype = C.c_int
-        L.pn_b200_solve_save_at_host.argtypes = [C.POINTER(Desc)] + [dp] * 16 + [C.c_int]
+        L.pn_b200_solve_save_at_host.argtypes = [C.POINTER(Desc)] + [dp] * 17 + [C.c_int]
         L.pn_b200_get_kernel_info.restype = C.c_int
         L.pn_b200_get_kernel_info.argtypes = [C.POINTER(Desc), C.POINTER(KernelInfo)]
         L.pn_b200_measure_fp64_peak.restype = C.c_int
         L.pn_b200_measure_fp64_peak.argtypes = [C.POINTER(C.c_double), vp]
         L.pn_b200_markov_sample.restype = C.c_int
         L.pn_b200_markov_sample.argtypes = [C.POINTER(Desc), vp, C.c_size_t, vp, C.c_uint64, C.c_int64, vp, vp]
+        L.pn_b200_log_marginal_likelihood.restype = C.c_int
+        L.pn_b200_log_marginal_likelihood.argtypes = [C.POINTER(Desc), vp, C.c_size_t, vp, vp, vp, vp, vp]
         L.pn_b200_set_profiling.restype = C.c_int
         L.pn_b200_set_profiling.argtypes = [C.c_int]
         L.pn_b200_get_last_timing.restype = C.c_int
@@ -270,6 +272,13 @@ class _HostPool:
 _host_pool = _HostPool()
 
 
+def _scale_shape(desc):
+    """output_scale: [B, K], or [B, K, d] for blockdiag (one scale per dimension)."""
+    if desc.factorisation == FACTORISATIONS["blockdiag"] and desc.d > 1:
+        return (desc.batch, desc.num_save_at, desc.d)
+    return (desc.batch, desc.num_save_at)
+
+
 def _host_empty(shape, dtype=np.float64):
     """Result buffer on the host: recycled page-locked memory for large results, plain numpy otherwise."""
     nbytes = int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize
@@ -298,6 +307,7 @@ def solve_host(desc, u0, params, tol, save_at, output_scale0, *, full=False, dev
     }
     mm = _host_empty((B, K, n, d)) if full else None
     mc = _host_empty(_chol_shape(desc)) if full else None
+    sc = _host_empty(_scale_shape(desc)) if full else None
     rec = bool(desc.flags & FLAG_RECORD)
     cap = desc.traj_capacity
     tt = _host_empty((cap, B)) if rec else None
@@ -306,13 +316,13 @@ def solve_host(desc, u0, params, tol, save_at, output_scale0, *, full=False, dev
     tl = _host_empty((B,), np.int64) if rec else None
     rc = lib().pn_b200_solve_save_at_host(
         C.byref(desc), _np_ptr(u0), _np_ptr(params), _np_ptr(tol), _np_ptr(save_at), _np_ptr(output_scale0),
-        _np_ptr(out["u"]), _np_ptr(out["u_std"]), _np_ptr(mm), _np_ptr(mc),
+        _np_ptr(out["u"]), _np_ptr(out["u_std"]), _np_ptr(mm), _np_ptr(mc), _np_ptr(sc),
         _np_ptr(out["n_accepted"]), _np_ptr(out["n_rejected"]), _np_ptr(out["status"]),
         _np_ptr(tt), _np_ptr(tu), _np_ptr(ts), _np_ptr(tl), C.c_int(device),
     )  # fmt: skip
     check(rc)
     if full:
-        out["marg_mean"], out["marg_chol"] = mm, mc
+        out["marg_mean"], out["marg_chol"], out["output_scale"] = mm, mc, sc
     if rec:
         out.update(traj_t=tt, traj_u=tu, traj_std=ts, traj_len=tl)
     return out
@@ -350,6 +360,7 @@ def solve_device(desc, u0, params, tol, save_at, output_scale0, *, full=False, w
         if full:
             out["marg_mean"] = torch.empty((B, K, n, d), **f64)
             out["marg_chol"] = torch.empty(_chol_shape(desc), **f64)
+            out["output_scale"] = torch.empty(_scale_shape(desc), **f64)
         if desc.flags & FLAG_RECORD:
             cap = desc.traj_capacity
             out["traj_t"] = torch.empty((cap, B), **f64)
@@ -364,6 +375,7 @@ def solve_device(desc, u0, params, tol, save_at, output_scale0, *, full=False, w
         rc = lib().pn_b200_solve_save_at(
             C.byref(desc), ptr(u0), ptr(params), ptr(tol), ptr(save_at), ptr(output_scale0),
             ptr(out["u"]), ptr(out["u_std"]), ptr(out.get("marg_mean")), ptr(out.get("marg_chol")),
+            ptr(out.get("output_scale")),
             ptr(out["n_accepted"]), ptr(out["n_rejected"]), ptr(out["status"]),
             ptr(out.get("traj_t")), ptr(out.get("traj_u")), ptr(out.get("traj_std")), ptr(out.get("traj_len")),
             C.c_void_p(workspace.data_ptr()), C.c_size_t(workspace.numel() * workspace.element_size()),

@@ -182,14 +182,15 @@ def _solve(vf, init, save_at, adaptive_solver, dt0, *, factorisation, return_mar
 
 def _solution(out, t_out, batched, return_marginals):
     sel = (lambda x: x) if batched else (lambda x: x[0])
-    marg = post = None
+    marg = post = scale = None
     if return_marginals:
+        scale = sel(out["output_scale"])
         marg = Normal(sel(out["marg_mean"]), sel(out["marg_chol"]))
         mm, mc = out["marg_mean"], out["marg_chol"]
         init = Normal(sel(mm[:, 1:]), sel(mc[:, 1:])) if batched else Normal(mm[0, 1:], mc[0, 1:])
         post = MarkovSeq(init, marg, out.get("_handle"))
     return Solution(
-        t=t_out, u=sel(out["u"]), u_std=sel(out["u_std"]), output_scale=None, marginals=marg, posterior=post,
+        t=t_out, u=sel(out["u"]), u_std=sel(out["u_std"]), output_scale=scale, marginals=marg, posterior=post,
         num_steps=sel(out["n_accepted"]), num_rejected=sel(out["n_rejected"]), status=sel(out["status"]),
     )  # fmt: skip
 

@@ -84,6 +84,9 @@ size_t pn_b200_workspace_bytes(const pn_b200_desc* desc);
  *   u, u_std      [B][K][d]     smoothed checkpoint means / marginal standard deviations
  *   marg_mean     [B][K][n][d] | NULL, marg_chol [B][K][n][n] | NULL   full marginals (n = nu+1);
  *                 blockdiag with d > 1: marg_chol is [B][K][d][n][n] (one factor per dimension)
+ *   output_scale  [B][K] | NULL the output scale every checkpoint carries (solution.output_scale:
+ *                 the calibrated sigma of the accepted step that reached or crossed it; entry 0 is
+ *                 output_scale0); blockdiag: [B][K][d], one scale per dimension
  *   n_accepted    [B][K]        cumulative accepted steps when checkpoint k was emitted
  *   n_rejected    [B], status [B]
  *   traj_*        PN_B200_FLAG_RECORD only: traj_t [cap][B], traj_u [cap][d][B], traj_std [cap][B],
@@ -92,7 +95,7 @@ size_t pn_b200_workspace_bytes(const pn_b200_desc* desc);
 int pn_b200_solve_save_at(const pn_b200_desc* desc, const double* u0, const double* params,
                           const double* tol, const double* save_at, const double* output_scale0,
                           double* u, double* u_std, double* marg_mean, double* marg_chol,
-                          int64_t* n_accepted, int64_t* n_rejected, int32_t* status, double* traj_t,
+                          double* output_scale, int64_t* n_accepted, int64_t* n_rejected, int32_t* status, double* traj_t,
                           double* traj_u, double* traj_std, int64_t* traj_len, void* workspace,
                           size_t workspace_bytes, void* cuda_stream);
 
@@ -104,7 +107,7 @@ int pn_b200_solve_save_at(const pn_b200_desc* desc, const double* u0, const doub
 int pn_b200_solve_save_at_host(const pn_b200_desc* desc, const double* u0, const double* params,
                                const double* tol, const double* save_at, const double* output_scale0,
                                double* u, double* u_std, double* marg_mean, double* marg_chol,
-                               int64_t* n_accepted, int64_t* n_rejected, int32_t* status, double* traj_t,
+                               double* output_scale, int64_t* n_accepted, int64_t* n_rejected, int32_t* status, double* traj_t,
                                double* traj_u, double* traj_std, int64_t* traj_len, int device);
 
 /*

@@ -473,3 +473,40 @@ def test_single_attempted_step_parity(cabi, oracle):
         np.testing.assert_array_equal(gpu["marg_mean"][0, 1].ravel(), step["mean"].ravel())
         np.testing.assert_array_equal(gpu["marg_chol"][0, 1].reshape(N, N), step["chol"][0])
         assert np.isfinite(step["error_norm"]) and step["dt_proposed"] > 0
+
+
+SCALE_CASES = [
+    # problem, d, nu, q, P, params, u0, save_at, oracle reduction_group, kwargs
+    ("logistic", 1, 3, 1, 2, (1.0, 1.0), np.array([[0.1]]), np.linspace(0, 2.5, 7), 0, dict(atol=1e-5, rtol=1e-5, dt0=0.1)),
+    ("van_der_pol", 1, 4, 2, 1, (1e3,), pu.van_der_pol_u0(), np.linspace(0, 6.3, 50), 0, dict(atol=1e-4, rtol=1e-4, fact="dense", corr="ts1")),
+    ("van_der_pol", 1, 2, 2, 1, (1e1,), pu.van_der_pol_u0(), np.linspace(0, 6.3, 20), 0, dict(atol=1e-4, rtol=1e-4, fact="dense", corr="ts1", calib="none")),
+    ("rigid_body", 3, 4, 1, 3, pu.RIGID_BODY_PARAMS, pu.rigid_body_u0(), np.linspace(0, 50, 9), 4, dict(atol=1e-9, rtol=1e-6, dt0=50.0, fact="blockdiag")),
+    ("pleiades", 14, 3, 2, 0, (), pu.pleiades_u0(), np.linspace(0, 3, 20), 16, dict(atol=1e-7, rtol=1e-4, dt0=0.1)),
+    ("rigid_body", 3, 4, 1, 3, pu.RIGID_BODY_PARAMS, pu.rigid_body_u0(), np.linspace(0, 50, 9), 0, dict(atol=1e-9, rtol=1e-6, dt0=50.0, fact="dense", corr="ts1")),
+    ("rigid_body", 3, 4, 1, 3, pu.RIGID_BODY_PARAMS, pu.rigid_body_u0(), np.linspace(0, 50, 9), 0, dict(atol=1e-9, rtol=1e-6, dt0=50.0, fact="dense", corr="ts1", strat="filter")),
+    ("brusselator", 64, 4, 1, 1, (0.02,), None, np.linspace(0, 2, 12), 128, dict(atol=1e-6, rtol=1e-6, dt0=0.01)),
+]
+
+
+@pytest.mark.parametrize("case", SCALE_CASES, ids=lambda c: f"{c[0]}-nu{c[2]}-{c[9].get('fact', 'isotropic')}-{c[9].get('strat', 'fixedpoint')}")
+def test_output_scale_at_the_checkpoints_bitwise_vs_oracle(cabi, oracle, case):
+    # solution.output_scale: the calibrated scale of the accepted step that reached
+    # or crossed each checkpoint; one per dimension for blockdiag
+    problem, d, nu, q, P, params, u0, save_at, group, kw = case
+    if u0 is None:
+        N = d // 2
+        u0 = np.concatenate([np.sin(2 * np.pi * np.linspace(0, 1, N)) + 1, 3 * np.ones(N)])[None]
+    kw = dict(kw, P=P)
+    K = len(save_at)
+    par = np.asarray(params, dtype=float)[None] if P else None
+    gpu = cabi.solve_host(_desc(cabi, problem, d, nu, q, 1, K, **kw), u0[None], par, None, save_at, None, full=True)
+    ora = oracle.solve_save_at_lml(_ocfg(oracle, problem, d, nu, q, reduction_group=group, **kw), u0, params, save_at,
+                                   np.zeros((K, d)), np.ones(K))  # fmt: skip
+    assert ora["status"] == 0 and gpu["status"][0] == 0
+    np.testing.assert_array_equal(gpu["u"][0], ora["u"])
+    np.testing.assert_array_equal(gpu["output_scale"][0].reshape(K, -1), ora["output_scale"])
+    assert gpu["output_scale"][0].reshape(K, -1)[0].tolist() == [1.0] * ora["output_scale"].shape[1]
+    if kw.get("calib") == "none":
+        assert (gpu["output_scale"] == 1.0).all()
+    else:
+        assert len(np.unique(gpu["output_scale"])) > K // 2
