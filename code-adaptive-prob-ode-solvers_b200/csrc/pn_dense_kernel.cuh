@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_kernel(const __grid_const
       for (int e = lane; e < Dn; e += 32) slot_base[e] = S_m[e];
       for (int e = lane; e < MAT; e += 32) slot_base[Dn + e] = 0.0;
     }
-    double t = a.save_at[0], dt_next = a.dt0, e_prev = 1.0, le_prev = 0.0;
+    double t = a.save_at[0], dt_next = a.dt0, le_prev = 0.0;
     double pend_t = 0.0, pend_sigma = 1.0, sigma_state = sigma0;
     int mode = MODE_STEP;
     long long k_next = 1, n_acc = 0, n_rej = 0, n_att = 0;
@@ -547,7 +547,6 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_kernel(const __grid_const
           dt_next = fac * dt;
           if (e_norm <= 1.0 || fixed_grid) {
             if (!fixed_grid) {
-              e_prev = e_norm;
               le_prev = le_now;
             }
             n_acc += 1;

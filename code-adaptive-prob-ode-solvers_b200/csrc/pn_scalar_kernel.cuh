@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
   // ---- per-lane persistent state --------------------------------------------------------
   bool have = false, exhausted = false;
   long long b = 0, vb = 0;
-  double t = 0.0, dt_next = 0.0, e_prev = 1.0, le_prev = 0.0, sigma_state = 1.0, sigma0 = 1.0;
+  double t = 0.0, dt_next = 0.0, le_prev = 0.0, sigma_state = 1.0, sigma0 = 1.0;
   double atol = a.atol, rtol = a.rtol;
   double par[P];
   int mode = MODE_STEP;
@@ -394,7 +394,6 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
         }
         t = a.save_at[0];
         dt_next = a.dt0;
-        e_prev = 1.0;
         le_prev = 0.0;
         sigma_state = sigma0;
         mode = MODE_STEP;
@@ -1081,7 +1080,6 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
         dt_next = fac * dt;
         if (e_norm <= 1.0 || fixed_grid) {
           if (!fixed_grid) {
-            e_prev = e_norm;
             le_prev = le_now;
           }
           n_acc += 1;
