@@ -510,3 +510,36 @@ def test_output_scale_at_the_checkpoints_bitwise_vs_oracle(cabi, oracle, case):
         assert (gpu["output_scale"] == 1.0).all()
     else:
         assert len(np.unique(gpu["output_scale"])) > K // 2
+
+
+@pytest.mark.parametrize("N", [1024, 2048])
+def test_wide_brusselator_largest_grids_bitwise_vs_oracle(cabi, oracle, N):
+    # BASELINE config 5's largest grid (N = 1024, d = 2048) and the kernel's maximum (d = 4096), a short
+    # interval so that the oracle finishes in seconds
+    d, K = 2 * N, 3
+    save_at = np.linspace(0.0, 0.002, K)
+    u0 = pu.brusselator_u0(N)
+    kw = dict(atol=1e-6, rtol=1e-6, dt0=1e-5, P=1)
+    gpu = cabi.solve_host(_desc(cabi, "brusselator", d, 4, 1, 2, K, **kw), np.tile(u0[None], (2, 1, 1)), np.array([[0.02], [0.03]]), None, save_at, None)
+    ocfg = _ocfg(oracle, "brusselator", d, 4, 1, reduction_group=128, **kw)
+    for b, alpha in enumerate((0.02, 0.03)):
+        ora = oracle.solve_save_at(ocfg, u0, [alpha], save_at)
+        assert ora["status"] == 0 and ora["n_accepted"][-1] > 20
+        _assert_bitwise({k: v[b] for k, v in gpu.items()}, ora)
+
+
+def test_empty_ensemble_minimal_grid_and_unsupported_sizes(cabi, oracle):
+    # B = 0: nothing to do, nothing written; K = 2 is the smallest grid; odd / oversized Brusselator
+    # dimensions and K < 2 are refused with the reference-style exceptions
+    save_at = np.array([0.0, 1.0])
+    empty = cabi.solve_host(_desc(cabi, "logistic", 1, 2, 1, 0, 2, P=2), np.zeros((0, 1, 1)), np.zeros((0, 2)), None, save_at, None)
+    assert empty["u"].shape == (0, 2, 1) and empty["status"].shape == (0,)
+    one = cabi.solve_host(_desc(cabi, "logistic", 1, 2, 1, 1, 2, P=2, atol=1e-4, rtol=1e-4, dt0=0.1), np.array([[[0.1]]]), np.array([[1.0, 1.0]]), None, save_at, None)
+    ora = oracle.solve_save_at(_ocfg(oracle, "logistic", 1, 2, 1, P=2, atol=1e-4, rtol=1e-4, dt0=0.1), np.array([[0.1]]), (1.0, 1.0), save_at)
+    _assert_bitwise({k: v[0] for k, v in one.items()}, ora)
+    with pytest.raises(NotImplementedError):
+        cabi.solve_host(_desc(cabi, "brusselator", 4098, 4, 1, 1, 2, P=1), np.zeros((1, 1, 4098)), np.array([[0.02]]), None, save_at, None)
+    with pytest.raises(NotImplementedError):
+        cabi.solve_host(_desc(cabi, "brusselator", 101, 4, 1, 1, 2, P=1), np.zeros((1, 1, 101)), np.array([[0.02]]), None, save_at, None)
+    with pytest.raises(ValueError):
+        cabi.solve_host(_desc(cabi, "logistic", 1, 2, 1, 1, 1, P=2), np.array([[[0.1]]]), np.array([[1.0, 1.0]]), None, save_at[:1], None)
