@@ -76,6 +76,9 @@ struct Plan {
   size_t ws_ticket = 256;  // header: work-queue ticket + stats (256 B), ordering histogram / cursors, order[B]
   size_t ws_cond = 0;      // bytes of conditionals
   size_t ws_wide = 0;      // wide kernels: per-member mean arrays
+  size_t ws_slice = 0;     // time-sliced scheduling: ready queues [G][B] + control words + parked states [B][ctx]
+  int slice_shift = 0;     // queue group of a member = (k_next - 1) >> slice_shift, G <= 63 groups
+  size_t ws_queue = 0;     // ... of which the ready queues (set to -1 before every launch)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -85,6 +88,10 @@ struct Plan {
 // removes most of the tail at the end of the persistent launch.  Scheduling only: results do not
 // depend on it.
 // ---------------------------------------------------------------------------------------
+// control block of the time-sliced scheduler: sw[2] (queue mask, finished members) + 64 (pop, push) pairs
+constexpr size_t SLICE_CONTROL_BYTES = 1024;
+constexpr int SLICE_MIN_CHECKPOINTS = 8;
+constexpr size_t SLICE_MAX_QUEUE_BYTES = (size_t)512 << 20;
 constexpr int ORDER_BUCKETS = 128;
 constexpr size_t WS_HIST_OFFSET = 256, WS_CURSOR_OFFSET = WS_HIST_OFFSET + ORDER_BUCKETS * 4;
 constexpr size_t WS_ORDER_OFFSET = WS_CURSOR_OFFSET + ORDER_BUCKETS * 4;
@@ -177,6 +184,20 @@ static int make_plan(const pn_b200_desc* d, Plan* p, bool need_device) {
     p->ws_cond = (size_t)d->batch * ((size_t)d->num_save_at * (p->k->slot_doubles + 2 * nd)) * sizeof(double);
     p->ws_wide = (size_t)d->batch * 3 * nd * sizeof(double);
   }
+  // time-sliced scheduling (pn_scalar_kernel.cuh: SolveArgs::slice): thread-per-IVP kernels, enough
+  // checkpoints to slice at, bounded queue memory
+  if (p->k->ctx_doubles > 0 && d->num_save_at >= SLICE_MIN_CHECKPOINTS && d->batch > 1 && d->batch < 0x7fffffffLL &&
+      !(d->flags & (PN_B200_FLAG_RECORD | PN_B200_FLAG_FIXED_GRID))) {
+    int shift = 0;
+    while (((d->num_save_at - 2) >> shift) > 62) ++shift;
+    const size_t groups = (size_t)((d->num_save_at - 2) >> shift) + 1;
+    const size_t queue = groups * d->batch * sizeof(int32_t);
+    if (queue <= SLICE_MAX_QUEUE_BYTES) {
+      p->slice_shift = shift;
+      p->ws_queue = (queue + 255) / 256 * 256;
+      p->ws_slice = p->ws_queue + SLICE_CONTROL_BYTES + (size_t)d->batch * p->k->ctx_doubles * sizeof(double);
+    }
+  }
   if (!need_device) return PN_B200_SUCCESS;
   int dev = 0;
   cudaError_t ce = cudaGetDevice(&dev);
@@ -194,6 +215,8 @@ static int make_plan(const pn_b200_desc* d, Plan* p, bool need_device) {
     ce = cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, cudaGetErrorString(ce));
     ce = cudaFuncSetAttribute(p->k->solve_func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
+    if (ce == cudaSuccess && p->k->solve_func_sliced)
+      ce = cudaFuncSetAttribute(p->k->solve_func_sliced, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
     if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce));
     int occ = 0;
     ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, p->k->solve_func, p->k->threads, p->smem);
@@ -256,7 +279,7 @@ int pn_b200_supported(const pn_b200_desc* desc) {
 size_t pn_b200_workspace_bytes(const pn_b200_desc* desc) {
   Plan p;
   if (make_plan(desc, &p, false)) return 0;
-  return p.ws_ticket + p.ws_cond + p.ws_wide;
+  return p.ws_ticket + p.ws_cond + p.ws_wide + p.ws_slice;
 }
 
 int pn_b200_get_kernel_info(const pn_b200_desc* desc, pn_b200_kernel_info* info) {
@@ -292,7 +315,8 @@ int pn_b200_solve_save_at(const pn_b200_desc* desc, const double* u0, const doub
   if (desc->num_params > 0 && !params) return fail(PN_B200_ERR_ARGUMENT, "params is null but num_params > 0");
   if ((desc->flags & PN_B200_FLAG_RECORD) && (!traj_t || !traj_u || !traj_std || !traj_len || desc->traj_capacity < 2))
     return fail(PN_B200_ERR_ARGUMENT, "trajectory recording needs traj buffers and traj_capacity >= 2");
-  if (!workspace || workspace_bytes < p.ws_ticket + p.ws_cond + p.ws_wide) return fail(PN_B200_ERR_WORKSPACE, "workspace too small");
+  if (!workspace || workspace_bytes < p.ws_ticket + p.ws_cond + p.ws_wide + p.ws_slice)
+    return fail(PN_B200_ERR_WORKSPACE, "workspace too small");
   cudaStream_t stream = (cudaStream_t)cuda_stream;
 
   SolveArgs a;
@@ -348,13 +372,33 @@ int pn_b200_solve_save_at(const pn_b200_desc* desc, const double* u0, const doub
     if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, std::string("ordering kernels: ") + cudaGetErrorString(ce));
     a.order = order;
   }
+  // time-sliced scheduling: uniform tolerances only (ragged ensembles get the longest-first order
+  // above instead), and only when the ensemble does not fit the resident lanes anyway
+  bool sliced = false;
+  if (p.ws_slice > 0 && p.k->launch_solve_sliced && !tol && desc->batch > (int64_t)p.grid * p.k->threads &&
+      !getenv("PN_B200_NO_SLICE")) {
+    char* base = (char*)workspace + p.ws_ticket + p.ws_cond + p.ws_wide;
+    ce = cudaMemsetAsync(base, 0xff, p.ws_queue, stream);
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(base + p.ws_queue, 0, SLICE_CONTROL_BYTES, stream);
+    if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, cudaGetErrorString(ce));
+    sliced = true;
+    long long quantum = SLICE_QUANTUM;
+    if (const char* q = getenv("PN_B200_SLICE_QUANTUM")) quantum = atoll(q);
+    if (quantum < 1 || (quantum & (quantum - 1))) return fail(PN_B200_ERR_ARGUMENT, "PN_B200_SLICE_QUANTUM must be a power of two");
+    a.slice_mask = quantum - 1;
+    a.slice_shift = p.slice_shift;
+    a.squeue = (int32_t*)base;
+    a.sw = (unsigned long long*)(base + p.ws_queue);
+    a.sq = (unsigned*)(a.sw + 2);
+    a.ctx = (double*)(base + p.ws_queue + SLICE_CONTROL_BYTES);
+  }
   const bool prof = g_profiling;
   if (prof && !g_ev_ready) {
     for (auto& e : g_ev) cudaEventCreate(&e);
     g_ev_ready = true;
   }
   if (prof) cudaEventRecord(g_ev[0], stream);
-  ce = p.k->launch_solve(a, p.grid, p.smem, stream);
+  ce = sliced ? p.k->launch_solve_sliced(a, p.grid, p.smem, stream) : p.k->launch_solve(a, p.grid, p.smem, stream);
   if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, std::string("solve kernel launch: ") + cudaGetErrorString(ce));
   if (prof) {
     cudaEventRecord(g_ev[1], stream);

@@ -29,9 +29,12 @@ struct KernelEntry {
   int threads;
   int group;          // lanes per IVP (1: thread per IVP)
   int dv;             // lanes per IVP that own state (workspace entries per member)
+  int ctx_doubles;    // doubles one parked member occupies (time-sliced scheduling); 0: not supported
   bool has_jac;
   const void* solve_func;
+  const void* solve_func_sliced;  // time-sliced variant of the same kernel (nullptr: none)
   cudaError_t (*launch_solve)(const SolveArgs&, int grid, size_t smem, cudaStream_t);
+  cudaError_t (*launch_solve_sliced)(const SolveArgs&, int grid, size_t smem, cudaStream_t);
   cudaError_t (*launch_smooth)(const SmoothArgs&, cudaStream_t);
   cudaError_t (*launch_sample)(const SampleArgs&, cudaStream_t);  // nullptr: family has no sampler yet
   cudaError_t (*launch_lml)(const LmlArgs&, cudaStream_t);        // nullptr: no likelihood kernel for this family
@@ -46,6 +49,12 @@ struct ScalarInstance {
   static constexpr int DV = (GROUP > 1) ? Prob::D : 1;
   static cudaError_t launch_solve(const SolveArgs& a, int grid, size_t smem, cudaStream_t s) {
     pn_scalar_kernel<Prob, NU, STRAT, GROUP, BDIAG, THREADS><<<grid, THREADS, smem, s>>>(a);
+    return cudaGetLastError();
+  }
+  // time-sliced scheduling: compiled for the thread-per-IVP fixed-point kernels (the checkpoint solver)
+  static constexpr bool SLICED = (GROUP == 1 && STRAT == 1);
+  static cudaError_t launch_solve_sliced(const SolveArgs& a, int grid, size_t smem, cudaStream_t s) {
+    pn_scalar_kernel<Prob, NU, STRAT, GROUP, BDIAG, THREADS, 0, SLICED ? 1 : 0><<<grid, THREADS, smem, s>>>(a);
     return cudaGetLastError();
   }
   static cudaError_t launch_smooth(const SmoothArgs& a, cudaStream_t s) {
@@ -80,6 +89,9 @@ struct ScalarInstance {
     e.P = Prob::P;
     e.slot_doubles = (STRAT == 1) ? Lay::SLOT_FIX : Lay::SLOT_FILT;
     e.smem_doubles = ((STRAT == 1) ? Lay::BW : 0) + Lay::PEND + Lay::MARG;
+    e.ctx_doubles = SLICED ? slice_ctx_doubles(Lay::BW, Lay::MARG) : 0;
+    e.solve_func_sliced = SLICED ? (const void*)&pn_scalar_kernel<Prob, NU, STRAT, GROUP, BDIAG, THREADS, 0, SLICED ? 1 : 0> : nullptr;
+    e.launch_solve_sliced = SLICED ? &launch_solve_sliced : nullptr;
     e.threads = THREADS;
     e.has_jac = Prob::HAS_JAC;
     e.solve_func = (const void*)&pn_scalar_kernel<Prob, NU, STRAT, GROUP, BDIAG, THREADS>;
@@ -110,6 +122,9 @@ struct DenseInstance {
     KernelEntry e;
     e.launch_sample = nullptr;
     e.launch_lml = nullptr;
+    e.ctx_doubles = 0;
+    e.solve_func_sliced = nullptr;
+    e.launch_solve_sliced = nullptr;
     e.family = FAMILY_DENSE;
     e.group = 32;
     e.dv = 1;
@@ -170,6 +185,9 @@ struct WideInstance {
     KernelEntry e;
     e.launch_sample = nullptr;
     e.launch_lml = nullptr;
+    e.ctx_doubles = 0;
+    e.solve_func_sliced = nullptr;
+    e.launch_solve_sliced = nullptr;
     e.family = FAMILY_WIDE;
     e.group = THREADS;
     e.dv = 1;

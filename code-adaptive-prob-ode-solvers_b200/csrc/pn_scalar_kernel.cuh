@@ -71,6 +71,23 @@ struct SolveArgs {
   // carry their own tolerances, so the members with the most steps start first and the launch does
   // not end on a tail of a few long solves.
   const long long* order;
+  // Time-sliced scheduling (SLICE = 1 instances of the thread-per-IVP kernel, uniform tolerances): a
+  // lane runs a member for a quantum of attempted steps, then parks it (state -> ctx) in the ready queue
+  // of the checkpoint interval it is in and takes the most lagging ready member instead.  All members
+  // then move through the checkpoints roughly in lockstep and finish together, so an ensemble that is a
+  // non-integer multiple of the resident lanes no longer ends on a half-empty wave.  Scheduling only:
+  // the arithmetic of a member is unchanged.  Fresh members (plain ticket) go before every parked one.
+  //   squeue [G][B]  rings of parked member ids, one per queue group g = (k_next - 1) >> slice_shift
+  //                  (-1 = position taken, id not stored yet); G <= 63
+  //   sq     [2 g]   pop counter, [2 g + 1] push counter of group g
+  //   sw     [0]     bit g: queue g may be non-empty; bit 63: no fresh member left;  [1] finished members
+  //   ctx    [B][CTX] parked states
+  long long slice_mask;  // quantum - 1 (quantum: attempted steps between two scheduling decisions, a power of two)
+  int32_t slice_shift;
+  int32_t* squeue;
+  unsigned* sq;
+  unsigned long long* sw;
+  double* ctx;
   // nullable [B][K][S]: the output scale carried by every checkpoint (solution.output_scale);
   // S = d for the blockdiag factorisation (one scale per dimension), else 1
   double* out_scale;
@@ -89,6 +106,126 @@ struct SolveArgs {
   // DFMA reads these entries as immediate constant operands.
   double lq[100];
 };
+
+// ---- time-sliced scheduling: cold paths, kept out of line so that they do not disturb the register
+// allocation of the step -----------------------------------------------------------------------
+// Default number of attempted steps between two scheduling decisions.  One park + take-over costs the
+// WARP about nine step iterations (cold code, L2 / DRAM round trips), so the quantum is long: two to
+// four slices per member are enough to fill the last wave (measured: 8192 -> 179 ms, 2048 -> 193 ms,
+// unsliced 208 ms on the 65,536-member Van der Pol ensemble).
+constexpr int SLICE_QUANTUM = 8192;
+constexpr unsigned long long SLICE_FRESH_GONE = 1ULL << 63;
+// doubles one parked member occupies: running conditional + hidden state + 8 scalars, padded to 16 bytes
+__host__ __device__ constexpr int slice_ctx_doubles(int nbw, int nstate) { return (nbw + nstate + 8 + 1) & ~1; }
+struct SliceScalars {
+  double t, dt_next, le_prev, sigma_state;
+  long long k_next, n_acc, n_rej, n_att;
+};
+
+// after a pop that may have emptied queue g (or found it empty): clear its bit, then repair the bit if
+// a push slipped in between (a pusher sets the bit itself after it has taken its position)
+static __device__ __forceinline__ void slice_mark_empty(const SolveArgs* a, int g) {
+  atomicAnd(a->sw, ~(1ULL << g));
+  const uint2 ht = __ldcg((const uint2*)(a->sq + 2 * g));
+  if (ht.x < ht.y) atomicOr(a->sw, 1ULL << g);
+}
+
+// Take the most lagging ready member: a fresh one while tickets last, else the head of the lowest
+// non-empty ready queue.  Returns the member or -1; *resume = 1 if it has a parked state.
+static __device__ __noinline__ long long slice_claim(const SolveArgs* a, int* resume, int* exhausted) {
+  const unsigned long long Bu = (unsigned long long)a->B;
+  *resume = 0;
+  const ulonglong2 w = __ldcg((const ulonglong2*)a->sw);  // (queue mask | fresh-gone flag, finished members)
+  unsigned long long m = w.x;
+  if (!(m & SLICE_FRESH_GONE)) {
+    const unsigned long long h = atomicAdd(a->ticket, 1ULL);
+    if (h < Bu) return (long long)h;
+    atomicOr(a->sw, SLICE_FRESH_GONE);
+  }
+  m &= ~SLICE_FRESH_GONE;
+  for (int tries = 0; m != 0 && tries < 6; ++tries) {
+    const int g = __ffsll((long long)m) - 1;
+    const uint2 ht = __ldcg((const uint2*)(a->sq + 2 * g));
+    if (ht.x >= ht.y) {  // stale bit
+      slice_mark_empty(a, g);
+      m &= ~(1ULL << g);
+      continue;
+    }
+    // Look before taking: a position whose id is not stored yet (its pusher sits between its two
+    // stores, possibly in this very warp) is treated as not ready -- nobody ever waits for anybody.
+    int* slot = a->squeue + (size_t)g * a->B + (ht.x % (unsigned)a->B);
+    const int c = __ldcg(slot);
+    if (c < 0) {
+      m &= ~(1ULL << g);
+      continue;
+    }
+    if (atomicCAS(a->sq + 2 * g, ht.x, ht.x + 1u) != ht.x) continue;  // somebody else took it: look again
+    *(volatile int*)slot = -1;  // the queues are rings: at most B members are parked at any time
+    if (ht.x + 1u >= ht.y) slice_mark_empty(a, g);
+    *resume = 1;
+    return (long long)c;
+  }
+  if (w.y >= Bu) *exhausted = 1;
+  return -1;
+}
+
+// Parked state -> shared memory + scalars.  All loads are issued before the first use: the parked
+// states are long out of L2 by the time they are needed again, so the latency must be paid once.
+template <int NBW, int NSTATE>
+static __device__ __noinline__ void slice_restore(const SolveArgs* a, long long b, double* sm_bw, double* sm_state, int stride,
+                                                  SliceScalars* io) {
+  __threadfence();
+  constexpr int TOT = slice_ctx_doubles(NBW, NSTATE);
+  const double2* cx = (const double2*)(a->ctx + (size_t)b * TOT);
+  double buf[TOT];
+#pragma unroll
+  for (int e = 0; e < TOT / 2; ++e) {
+    const double2 v = __ldcg(cx + e);
+    buf[2 * e] = v.x;
+    buf[2 * e + 1] = v.y;
+  }
+#pragma unroll
+  for (int e = 0; e < NBW; ++e) sm_bw[e * stride] = buf[e];
+#pragma unroll
+  for (int e = 0; e < NSTATE; ++e) sm_state[e * stride] = buf[NBW + e];
+  io->t = buf[NBW + NSTATE];
+  io->dt_next = buf[NBW + NSTATE + 1];
+  io->le_prev = buf[NBW + NSTATE + 2];
+  io->sigma_state = buf[NBW + NSTATE + 3];
+  io->k_next = __double_as_longlong(buf[NBW + NSTATE + 4]);
+  io->n_acc = __double_as_longlong(buf[NBW + NSTATE + 5]);
+  io->n_rej = __double_as_longlong(buf[NBW + NSTATE + 6]);
+  io->n_att = __double_as_longlong(buf[NBW + NSTATE + 7]);
+}
+
+// A member has used up its quantum of attempted steps while in queue group g (its checkpoint interval,
+// coarsened to at most 63 groups).  If a fresh member or a ready member of a group <= g is waiting, park
+// this one and report 1 (the lane then takes the waiting one); else the lane keeps it.
+static __device__ __noinline__ int slice_park_if_waiting(const SolveArgs* a, long long b, int g, const double* sm_bw, int nbw,
+                                                         const double* sm_state, int nstate, int stride,
+                                                         const SliceScalars* io) {
+  const unsigned long long m = __ldcg(a->sw);
+  const unsigned long long upto = (g >= 62) ? ~SLICE_FRESH_GONE : ((2ULL << g) - 1ULL);
+  if ((m & SLICE_FRESH_GONE) && !(m & upto)) return 0;
+  double* cx = a->ctx + (size_t)b * slice_ctx_doubles(nbw, nstate);
+  for (int e = 0; e < nbw; ++e) cx[e] = sm_bw[e * stride];
+  for (int e = 0; e < nstate; ++e) cx[nbw + e] = sm_state[e * stride];
+  cx += nbw + nstate;
+  cx[0] = io->t;
+  cx[1] = io->dt_next;
+  cx[2] = io->le_prev;
+  cx[3] = io->sigma_state;
+  long long* ci = (long long*)cx + 4;
+  ci[0] = io->k_next;
+  ci[1] = io->n_acc;
+  ci[2] = io->n_rej;
+  ci[3] = io->n_att;
+  __threadfence();
+  const unsigned pos = atomicAdd(a->sq + 2 * g + 1, 1u);
+  *(volatile int*)(a->squeue + (size_t)g * a->B + (pos % (unsigned)a->B)) = (int)b;
+  atomicOr(a->sw, 1ULL << g);
+  return 1;
+}
 
 template <int N>
 struct Binom {
@@ -203,7 +340,7 @@ struct GroupVf<Brusselator<NPTS>, GROUP> {
 //           same factor arithmetic as a thread-per-IVP lane; the n x d mean arrays live in global
 //           memory (L2 resident) and each thread owns the columns c = tid, tid + THREADS, ...;
 //           norms are reduced over the CTA.  Prob::D is a dummy (1) in this mode.
-template <class Prob, int NU, int STRAT, int GROUP, int BDIAG, int THREADS, int WIDE = 0>
+template <class Prob, int NU, int STRAT, int GROUP, int BDIAG, int THREADS, int WIDE = 0, int SLICE = 0>
 __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const __grid_constant__ SolveArgs a) {
   constexpr int N = NU + 1, DT = Prob::D, D = (GROUP > 1) ? 1 : DT, Q = Prob::Q, P = (Prob::P > 0 ? Prob::P : 1);
   constexpr int DV = (GROUP > 1) ? DT : 1;  // lanes ("virtual members") per IVP that own state
@@ -263,6 +400,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
 
   // ---- per-lane persistent state --------------------------------------------------------
   bool have = false, exhausted = false;
+  static_assert(!SLICE || (GROUP == 1 && !WIDE), "time-sliced scheduling: thread-per-IVP kernels only");
   long long b = 0, vb = 0;
   double t = 0.0, dt_next = 0.0, le_prev = 0.0, sigma_state = 1.0, sigma0 = 1.0;
   double atol = a.atol, rtol = a.rtol;
@@ -289,7 +427,15 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
     // ---- fetch a member ----------------------------------------------------------------
     if (!have && !exhausted) {
       unsigned long long tk = 0;
-      if constexpr (WIDE) {
+      bool resume = false, claimed_none = false;
+      if constexpr (SLICE) {
+        int rs = 0, ex = 0;
+        const long long c = slice_claim(&a, &rs, &ex);
+        resume = rs != 0;
+        exhausted = ex != 0;
+        claimed_none = c < 0;
+        tk = claimed_none ? (unsigned long long)a.B : (unsigned long long)c;
+      } else if constexpr (WIDE) {
         __shared__ unsigned long long s_ticket;
         __syncthreads();
         if (tid == 0) s_ticket = atomicAdd(a.ticket, 1ULL);
@@ -300,7 +446,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
         if (GROUP > 1) tk = __shfl_sync(gmask, tk, base);
       }
       if (tk < (unsigned long long)a.B) {
-        b = a.order ? a.order[tk] : (long long)tk;
+        b = (a.order && !SLICE) ? a.order[tk] : (long long)tk;
         vb = WIDE ? 0 : (b * DV + ((GROUP > 1 && real) ? sub : 0));
         have = true;
         double u0[Q * DT];
@@ -313,6 +459,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
         atol = a.tol ? a.tol[2 * b] : a.atol;
         rtol = a.tol ? a.tol[2 * b + 1] : a.rtol;
         sigma0 = a.sigma0 ? a.sigma0[b] : 1.0;
+        if (!resume) {
         if constexpr (WIDE) {
           Wm = a.wide_mean + (size_t)b * 3 * N * wd;
           Wg = Wm + (size_t)N * wd;
@@ -422,7 +569,21 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
             for (int j = 0; j <= i; ++j) a.cond[(long long)vb * a.K * SLOT + N * D + Lay::tri(i, j)] = 0.0;
           }
         }
-      } else {
+        } else if constexpr (SLICE) {
+          // take over a member another lane parked at a checkpoint
+          SliceScalars io;
+          slice_restore<(FIX ? Lay::BW : 0), Lay::MARG>(&a, b, s_bw + tid, s_state + tid, THREADS, &io);
+          t = io.t;
+          dt_next = io.dt_next;
+          le_prev = io.le_prev;
+          sigma_state = io.sigma_state;
+          k_next = io.k_next;
+          n_acc = io.n_acc;
+          n_rej = io.n_rej;
+          n_att = io.n_att;
+          mode = MODE_STEP;
+        }
+      } else if (!claimed_none) {
         exhausted = true;
       }
     }
@@ -434,7 +595,11 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
     const unsigned active = __ballot_sync(0xffffffffu, have);
 #else
     const unsigned active = __ballot_sync(0xffffffffu, have);
-    if (active == 0u) break;
+    if (active == 0u) {
+      if (!SLICE || __all_sync(0xffffffffu, exhausted)) break;
+      __nanosleep(5000);  // members are still running elsewhere and may yet be parked
+      continue;
+    }
 #endif
     stat_warp_iters += 1;
     stat_lane_iters += __popc(active);
@@ -1071,6 +1236,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
     bool finished = false;
     int st = 0;
     const bool fixed_grid = (a.flags & FLAG_FIXED_GRID) != 0;
+    const bool attempted = (mode == MODE_STEP);
     if (mode == MODE_STEP) {
       n_att += 1;
       if (e_norm != e_norm && !fixed_grid) {
@@ -1184,6 +1350,17 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
       }
       k_next += 1;
       after_checkpoint(finished);
+    }
+    if constexpr (SLICE) {
+      // the quantum boundaries of different members are staggered (b * 7919): lanes that started together
+      // would otherwise all reach the queues in the same iteration
+      if (!finished && attempted && mode == MODE_STEP && ((n_att + b * 7919LL) & a.slice_mask) == 0) {
+        const SliceScalars io = {t, dt_next, le_prev, sigma_state, k_next, n_acc, n_rej, n_att};
+        if (slice_park_if_waiting(&a, b, (int)(k_next - 1) >> a.slice_shift, s_bw + tid, FIX ? Lay::BW : 0, s_state + tid,
+                                  Lay::MARG, THREADS, &io))
+          have = false;
+      }
+      if (finished) atomicAdd(a.sw + 1, 1ULL);
     }
     if (finished) {
       if (leader) {

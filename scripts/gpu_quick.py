@@ -24,7 +24,9 @@ for it in range(3):
     ms = e0.elapsed_time(e1)
     acc = out["n_accepted"][:, -1].double(); rej = out["n_rejected"].double()
     att = (acc.sum() + rej.sum()).item()
-    st = out["_workspace"][:8].cpu().numpy()
+    st = out["_workspace"][:16].cpu().numpy()
+    if st[9] > 0:
+        print(f"   slice: claims={st[9]:.3e} avg {st[8]/max(st[9],1):.0f} cyc; restores={st[11]:.3e} avg {st[10]/max(st[11],1):.0f} cyc; leaves={st[13]:.3e} avg {st[12]/max(st[13],1):.0f} cyc, parked={st[14]:.3e}")
     print(f"   stats: warp_iters={st[1]:.4e} lane_iters={st[2]:.4e} util={st[2]/(32*st[1]):.3f} interp_frac={st[3]/st[2]:.4f} max_warp_cycles={st[4]:.4e} -> {st[4]/ms/1e6:.3f} GHz-equivalent")
     print(f"iter {it}: {ms:.2f} ms  solves/s={B/ms*1e3:.0f}  attempts={att:.3e}  attempts/s={att/ms*1e3:.3e} acc mean={acc.mean().item():.1f} rej mean={rej.mean().item():.1f} status_bad={(out['status']!=0).sum().item()}")
 print("fp64 peak TF", _cabi.measure_fp64_peak())

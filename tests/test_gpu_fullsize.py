@@ -75,3 +75,29 @@ def test_solution_stays_on_the_limit_cycle_and_agrees_with_a_tighter_solve(full_
     # away from the relaxation jumps (|u'| ~ 1e3) the 1e-6 solve is within ~1e-4 of the 1e-9 one
     err = np.abs(tight["u"] - res["u"][idx])[:, :, 0]
     assert np.median(err) < 1e-5 and np.quantile(err, 0.9) < 1e-3
+
+
+def test_time_sliced_scheduling_does_not_change_a_single_bit(full_run, monkeypatch):
+    # 65,536 members on 37,888 resident lanes: the launch above ran time-sliced (members are parked
+    # and taken over by other lanes).  Unsliced, and sliced with a tiny quantum (hundreds of hand-overs
+    # per member), must give the same bits.
+    import torch
+
+    _cabi, desc, u0, par, save_at, res = full_run
+    dev = torch.device("cuda:0")
+    B = 40960  # just above the resident lanes: still sliced, cheaper to repeat
+    d2 = _cabi.Desc(*[getattr(desc, n) for n, _ in _cabi.Desc._fields_])
+    d2.batch = B
+    args = (torch.as_tensor(u0[:B], device=dev), torch.as_tensor(par[:B], device=dev), None, torch.as_tensor(save_at, device=dev), None)
+    runs = {}
+    for name, env in (("unsliced", {"PN_B200_NO_SLICE": "1"}), ("quantum64", {"PN_B200_SLICE_QUANTUM": "64"}), ("default", {})):
+        for k in ("PN_B200_NO_SLICE", "PN_B200_SLICE_QUANTUM"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        out = _cabi.solve_device(d2, *args, full=True)
+        runs[name] = {k: v.cpu().numpy() for k, v in out.items() if not k.startswith("_")}
+    for name in ("unsliced", "quantum64", "default"):
+        for key in ("u", "u_std", "n_accepted", "n_rejected", "status", "marg_mean", "marg_chol", "output_scale"):
+            np.testing.assert_array_equal(runs[name][key], runs["unsliced"][key], err_msg=f"{name}:{key}")
+        np.testing.assert_array_equal(runs[name]["u"], res["u"][:B])
