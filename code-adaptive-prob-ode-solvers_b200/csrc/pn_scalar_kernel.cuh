@@ -126,8 +126,19 @@ struct SliceScalars {
 // a push slipped in between (a pusher sets the bit itself after it has taken its position)
 static __device__ __forceinline__ void slice_mark_empty(const SolveArgs* a, int g) {
   atomicAnd(a->sw, ~(1ULL << g));
+  __threadfence();  // the re-read must not overtake the clear: a push + set in between would be wiped out
   const uint2 ht = __ldcg((const uint2*)(a->sq + 2 * g));
   if (ht.x < ht.y) atomicOr(a->sw, 1ULL << g);
+}
+
+// Safety net, run by warps that have nothing to do: rebuild the "may be non-empty" bits from the
+// counters themselves, so that a parked member can never stay invisible (stale set bits are harmless,
+// the next taker clears them).
+static __device__ __noinline__ void slice_repair(const SolveArgs* a, int groups) {
+  for (int g = 0; g < groups; ++g) {
+    const uint2 ht = __ldcg((const uint2*)(a->sq + 2 * g));
+    if (ht.x < ht.y) atomicOr(a->sw, 1ULL << g);
+  }
 }
 
 // Take the most lagging ready member: a fresh one while tickets last, else the head of the lowest
@@ -223,8 +234,22 @@ static __device__ __noinline__ int slice_park_if_waiting(const SolveArgs* a, lon
   __threadfence();
   const unsigned pos = atomicAdd(a->sq + 2 * g + 1, 1u);
   *(volatile int*)(a->squeue + (size_t)g * a->B + (pos % (unsigned)a->B)) = (int)b;
+  __threadfence();
   atomicOr(a->sw, 1ULL << g);
   return 1;
+}
+
+// Long members: keep the number of hand-overs per member bounded (about eight) whatever its length.
+// The total number of attempted steps is extrapolated from the part of [t0, t1] covered so far and
+// the quantum grows to about an eighth of it (a finer one was measured slower: every hand-over stalls
+// the warp).  Evaluated at multiples of the base quantum only.
+static __device__ __noinline__ bool slice_quantum_reached(const SolveArgs& a, double t, long long n_att, long long b) {
+  const double t0 = a.save_at[0], t1 = a.save_at[a.K - 1];
+  const double frac = fmax((t - t0) / (t1 - t0), 1e-3);
+  const double target = 0.125 * (double)n_att / frac;
+  long long q = a.slice_mask + 1;
+  while ((double)q < target && q < (1LL << 40)) q <<= 1;
+  return ((n_att + b * 7919LL) & (q - 1)) == 0;
 }
 
 template <int N>
@@ -597,6 +622,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
     const unsigned active = __ballot_sync(0xffffffffu, have);
     if (active == 0u) {
       if (!SLICE || __all_sync(0xffffffffu, exhausted)) break;
+      if ((threadIdx.x & 31) == 0) slice_repair(&a, (int)((a.K - 2) >> a.slice_shift) + 1);
       __nanosleep(5000);  // members are still running elsewhere and may yet be parked
       continue;
     }
@@ -1354,7 +1380,8 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
     if constexpr (SLICE) {
       // the quantum boundaries of different members are staggered (b * 7919): lanes that started together
       // would otherwise all reach the queues in the same iteration
-      if (!finished && attempted && mode == MODE_STEP && ((n_att + b * 7919LL) & a.slice_mask) == 0) {
+      if (!finished && attempted && mode == MODE_STEP && ((n_att + b * 7919LL) & a.slice_mask) == 0 &&
+          slice_quantum_reached(a, t, n_att, b)) {
         const SliceScalars io = {t, dt_next, le_prev, sigma_state, k_next, n_acc, n_rej, n_att};
         if (slice_park_if_waiting(&a, b, (int)(k_next - 1) >> a.slice_shift, s_bw + tid, FIX ? Lay::BW : 0, s_state + tid,
                                   Lay::MARG, THREADS, &io))
