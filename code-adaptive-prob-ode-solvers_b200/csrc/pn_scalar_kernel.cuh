@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
   };
 
   // ---- per-lane persistent state --------------------------------------------------------
-  bool have = false, exhausted = false;
+  bool have = false, exhausted = false, poll_now = true;
   static_assert(!SLICE || (GROUP == 1 && !WIDE), "time-sliced scheduling: thread-per-IVP kernels only");
   long long b = 0, vb = 0;
   double t = 0.0, dt_next = 0.0, le_prev = 0.0, sigma_state = 1.0, sigma0 = 1.0;
@@ -450,7 +450,9 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
 
   for (;;) {
     // ---- fetch a member ----------------------------------------------------------------
-    if (!have && !exhausted) {
+    // SLICE: a lane that has just lost its member looks for the next one at once; after an unsuccessful
+    // look it only polls every eighth iteration (a poll is an L2 round trip that stalls the whole warp)
+    if (!have && !exhausted && (!SLICE || poll_now || (stat_warp_iters & 7ULL) == 0)) {
       unsigned long long tk = 0;
       bool resume = false, claimed_none = false;
       if constexpr (SLICE) {
@@ -459,6 +461,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
         resume = rs != 0;
         exhausted = ex != 0;
         claimed_none = c < 0;
+        poll_now = false;
         tk = claimed_none ? (unsigned long long)a.B : (unsigned long long)c;
       } else if constexpr (WIDE) {
         __shared__ unsigned long long s_ticket;
@@ -624,6 +627,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
       if (!SLICE || __all_sync(0xffffffffu, exhausted)) break;
       if ((threadIdx.x & 31) == 0) slice_repair(&a, (int)((a.K - 2) >> a.slice_shift) + 1);
       __nanosleep(5000);  // members are still running elsewhere and may yet be parked
+      poll_now = true;    // (this warp's iteration counter stands still while it has no member)
       continue;
     }
 #endif
@@ -1384,10 +1388,15 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
           slice_quantum_reached(a, t, n_att, b)) {
         const SliceScalars io = {t, dt_next, le_prev, sigma_state, k_next, n_acc, n_rej, n_att};
         if (slice_park_if_waiting(&a, b, (int)(k_next - 1) >> a.slice_shift, s_bw + tid, FIX ? Lay::BW : 0, s_state + tid,
-                                  Lay::MARG, THREADS, &io))
+                                  Lay::MARG, THREADS, &io)) {
           have = false;
+          poll_now = true;
+        }
       }
-      if (finished) atomicAdd(a.sw + 1, 1ULL);
+      if (finished) {
+        atomicAdd(a.sw + 1, 1ULL);
+        poll_now = true;
+      }
     }
     if (finished) {
       if (leader) {
