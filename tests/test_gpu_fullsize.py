@@ -101,3 +101,40 @@ def test_time_sliced_scheduling_does_not_change_a_single_bit(full_run, monkeypat
         for key in ("u", "u_std", "n_accepted", "n_rejected", "status", "marg_mean", "marg_chol", "output_scale"):
             np.testing.assert_array_equal(runs[name][key], runs["unsliced"][key], err_msg=f"{name}:{key}")
         np.testing.assert_array_equal(runs[name]["u"], res["u"][:B])
+
+
+@pytest.mark.parametrize("problem,d,nu,q,P", [("rigid_body", 3, 4, 1, 3), ("logistic", 1, 3, 1, 2), ("three_body", 2, 4, 2, 1)])
+def test_time_sliced_scheduling_other_problems(monkeypatch, problem, d, nu, q, P):
+    # the scheduler parks (running conditional + hidden state + 8 scalars) per member: sizes differ per
+    # problem and order (odd totals are padded).  40,960 members, uniform tolerance, small quantum.
+    import torch
+
+    import problems_util as pu
+    from odecheckpts_b200 import _cabi
+
+    dev = torch.device("cuda:0")
+    B, K = 40960, 9
+    rng = np.random.default_rng(11)
+    if problem == "rigid_body":
+        u0 = (np.array([1.0, 0.0, 0.9]) + 0.05 * rng.standard_normal((B, 3)))[:, None, :]
+        par, t1, tol, dt0 = np.tile(np.asarray(pu.RIGID_BODY_PARAMS), (B, 1)), 10.0, 1e-6, 0.1
+    elif problem == "logistic":
+        u0 = (0.05 + 0.1 * rng.random((B, 1)))[:, None, :]
+        par, t1, tol, dt0 = np.tile([1.0, 1.0], (B, 1)), 2.5, 1e-9, 0.1
+    else:
+        u0 = pu.three_body_u0()[None] * (1.0 + 1e-7 * rng.standard_normal((B, 2, 2)))  # (the orbit starts 6e-3 from the second body)
+        par, t1, tol, dt0 = np.full((B, 1), pu.THREE_BODY_MU), 3.0, 1e-7, 0.01
+    desc = _cabi.Desc(_cabi.PROBLEM_IDS[problem], d, nu, q, 0, 0, 1, 1, tol, tol, dt0, 0.95, 0.2, 10.0, 0.3, 0.4, B, K, 20000, P, 0, 0)
+    T = lambda x: torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float64, device=dev)  # noqa: E731
+    args = (T(u0), T(par), None, T(np.linspace(0.0, t1, K)), None)
+    runs = {}
+    for name, env in (("unsliced", {"PN_B200_NO_SLICE": "1"}), ("sliced", {"PN_B200_SLICE_QUANTUM": "16"})):
+        for k in ("PN_B200_NO_SLICE", "PN_B200_SLICE_QUANTUM"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        out = _cabi.solve_device(desc, *args, full=True)
+        runs[name] = {k: v.cpu().numpy() for k, v in out.items() if not k.startswith("_")}
+    assert (runs["unsliced"]["status"] == 0).all() and runs["unsliced"]["n_accepted"][:, -1].min() > 20
+    for key in ("u", "u_std", "n_accepted", "n_rejected", "status", "marg_mean", "marg_chol", "output_scale"):
+        np.testing.assert_array_equal(runs["sliced"][key], runs["unsliced"][key], err_msg=key)
