@@ -46,6 +46,17 @@ def test_supported_and_workspace_queries_need_no_gpu():
     slot = (n * n + n * D + n * (n + 1) // 2) + (n * D + n * (n + 1) // 2)
     header = (256 + 2 * 128 * 4 + B * 8 + 255) // 256 * 256  # ticket + stats, ordering histogram / cursors, order[B]
     assert _cabi.workspace_bytes(d) == header + K * slot * B * 8  # [B][K][slot]
+    # enough checkpoints for the time-sliced scheduler (fixed-point thread-per-IVP kernels): + ready queues
+    # [K-1 groups][B] int32, a 1 KB control block, parked states [B][running conditional + state + 8 scalars]
+    K2, B2 = 50, 1000
+    header2 = (256 + 2 * 128 * 4 + B2 * 8 + 255) // 256 * 256
+    queues = ((K2 - 1) * B2 * 4 + 255) // 256 * 256
+    ctx = ((n * n + n * D + n * (n + 1) // 2) + (n * D + n * (n + 1) // 2) + 8 + 1) // 2 * 2
+    assert _cabi.workspace_bytes(_desc(_cabi, batch=B2, num_save_at=K2)) == header2 + K2 * slot * B2 * 8 + queues + 1024 + B2 * ctx * 8
+    # ... but not for the filter strategy, trajectory recording or fixed grids
+    slot_f = n * D + n * (n + 1) // 2
+    assert _cabi.workspace_bytes(_desc(_cabi, batch=B2, num_save_at=K2, strategy=0)) == header2 + K2 * slot_f * B2 * 8
+    assert _cabi.workspace_bytes(_desc(_cabi, batch=B2, num_save_at=K2, flags=1)) == header2 + K2 * slot * B2 * 8
     assert not _cabi.supported(_desc(_cabi, problem=3, d=14))  # Pleiades has no thread-per-IVP kernel
     assert not _cabi.supported(_desc(_cabi, factorisation=0))  # isotropic + ts1 is not a valid model
     assert not _cabi.supported(_desc(_cabi, nu=9))
