@@ -146,3 +146,24 @@ def test_learn_ode_style_likelihood_through_the_builder_api(oracle):
             taylor.odejet_padded_scan(lambda *y: vf(*y, t=0.0), (y0, dy0), num=3), np.ones(())),
             save_at=save_at, dt0=0.1, adaptive_solver=asolver)  # fmt: skip
         stats.log_marginal_likelihood(data, standard_deviation=std, posterior=plain.posterior)
+
+
+def test_oracle_output_scale_per_checkpoint(oracle):
+    # solution.output_scale: entry 0 is the initial scale; the uncalibrated solver carries it unchanged,
+    # the dynamic solver carries the calibrated scale of the step that reached / crossed each checkpoint
+    save_at = np.linspace(0.0, 3.0, 8)
+    u0, params = np.array([[2.0], [0.0]]), (10.0,)
+    for calib in ("none", "dynamic"):
+        cfg = oracle.make_config("van_der_pol", 1, 4, 2, factorisation="dense", correction="ts1", calibration=calib,
+                                 atol=1e-5, rtol=1e-5, dt0=0.1, num_params=1)  # fmt: skip
+        res = oracle.solve_save_at_lml(cfg, u0, params, save_at, np.zeros((8, 1)), np.ones(8), output_scale0=2.5)
+        scale = res["output_scale"][:, 0]
+        assert scale[0] == 2.5
+        if calib == "none":
+            assert (scale == 2.5).all()
+        else:
+            assert (scale[1:] > 0).all() and len(np.unique(scale)) == 8
+    # blockdiag: one scale per dimension
+    cfg = oracle.make_config("rigid_body", 3, 3, 1, factorisation="blockdiag", atol=1e-6, rtol=1e-6, dt0=0.1, num_params=3)
+    res = oracle.solve_save_at_lml(cfg, np.array([[1.0, 0.0, 0.9]]), pu.RIGID_BODY_PARAMS, save_at, np.zeros((8, 3)), np.ones(8))
+    assert res["output_scale"].shape == (8, 3) and (np.abs(np.diff(res["output_scale"][1:], axis=1)) > 0).any()
