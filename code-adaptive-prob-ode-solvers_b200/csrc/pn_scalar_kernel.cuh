@@ -29,7 +29,12 @@
 //   * Only the first n columns of the 2n x 2n fixed-point block matrix are triangularised; the
 //     lower-right block is used as a full square-root factor and the merge re-triangularises.
 //   * Lanes pull members from a global atomic ticket, so differing step counts (tolerance
-//     sweeps) never idle a lane while work remains.
+//     sweeps) never idle a lane while work remains; members that carry their own tolerances are
+//     handed out tightest first (SolveArgs::order).
+//   * SLICE = 1 instances time-slice the members (see SolveArgs::slice_mask and the slice_* helpers):
+//     a member is parked after a quantum of attempted steps when a more lagging one is ready, so all
+//     members finish together and an ensemble of 1.73 x the resident lanes does not end on a
+//     half-empty wave.  The helpers are out of line: the step's register allocation is untouched.
 //   * HBM traffic: inputs once per member; per checkpoint one backward conditional into the
 //     member-major workspace [member][checkpoint][element] (a lane's slot is contiguous, so its
 //     stores fill whole sectors even when the lanes of a warp cross checkpoints at different times).
