@@ -621,12 +621,6 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
       }
     }
     // warp-level vote keeps the loop convergent; the lane counts feed the utilisation statistics
-#ifdef PN_CTA_LOCKSTEP
-    // CTA-wide lockstep: the 4 warps of a CTA sit on the 4 SM sub-partitions and fetch the same
-    // instructions at the same time (one instruction stream per CTA instead of one per warp)
-    if (!__syncthreads_or(have)) break;
-    const unsigned active = __ballot_sync(0xffffffffu, have);
-#else
     const unsigned active = __ballot_sync(0xffffffffu, have);
     if (active == 0u) {
       if (!SLICE || __all_sync(0xffffffffu, exhausted)) break;
@@ -635,7 +629,6 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
       poll_now = true;    // (this warp's iteration counter stands still while it has no member)
       continue;
     }
-#endif
     stat_warp_iters += 1;
     stat_lane_iters += __popc(active);
     stat_interp_iters += __popc(__ballot_sync(0xffffffffu, have && mode != MODE_STEP));
