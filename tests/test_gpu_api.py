@@ -193,3 +193,36 @@ def test_solve_via_interpolate_drop_in_matches_the_reference_goldens(goldens):
     sol, aux = fun(u0, params)
     assert len(aux["u0_solve"]) == 4158
     assert abs(np.linalg.norm(sol - ref) / np.sqrt(ref.size) / goldens["rigid_interp_nu2_precision"][-1] - 1.0) < 1e-3
+
+
+@pytest.mark.parametrize("m0", ["ts0-2", "ts0-4"])
+@pytest.mark.parametrize("m1", ["bosh3", "tsit5"])
+@pytest.mark.parametrize("which", ["checkpoint", "interpolate"])
+def test_two_solvers_return_the_same_solution(oracle, m0, m1, which):
+    # the reference's own test (tests/test_ivpsolvers.py:11-52), parametrisation for parametrisation; the
+    # diffrax competitors (out of scope) are stood in for by scipy's Runge-Kutta pairs of the
+    # same orders (Bogacki-Shampine 3(2) = RK23, a 5(4) pair = RK45) on the oracle's vector field
+    import scipy.integrate
+
+    from odecheckpts_b200 import ivps, ivpsolvers
+
+    vf, u0, time_span, args = ivps.logistic()
+    dt0 = 0.1
+    atol, rtol = 1e-3, 1e-3
+    save_at = np.linspace(*time_span, num=5)
+    u0_like = u0[0]
+    solver1 = ivpsolvers.solve if which == "checkpoint" else ivpsolvers.solve_via_interpolate
+    solve1 = solver1(m0, vf, u0_like, save_at, dt0=dt0, atol=atol, rtol=rtol)
+    solution1, aux1 = solve1(u0, args)
+
+    def solve2(u0_, p):
+        (init,) = u0_
+        f = lambda t, y: oracle.vf("logistic", y.reshape(1, -1), list(p), t=t)  # noqa: E731
+        sol = scipy.integrate.solve_ivp(f, (save_at[0], save_at[-1]), np.atleast_1d(init), t_eval=save_at, first_step=dt0,
+                                        method={"bosh3": "RK23", "tsit5": "RK45"}[m1], atol=atol, rtol=rtol)  # fmt: skip
+        return sol.y.T, {"solution": sol, "u0_solve": sol.y.T}
+
+    solution2, aux2 = solve2(u0, args)
+    assert "u0_solve" in aux1.keys()
+    assert "u0_solve" in aux2.keys()
+    assert np.allclose(solution1, solution2, atol=np.sqrt(atol), rtol=np.sqrt(rtol))
