@@ -881,8 +881,15 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
         }
       }
     }
+    // Program order of the two blocks that are off the step-size chain (merge of the backward conditional,
+    // QR of the corrected factor).  Thread-per-IVP kernels run them AFTER the error norm and the PI
+    // controller: the controller's serial sqrt -> log -> exp chain then overlaps with their independent
+    // work (-2 % on the headline kernel).  The lane-per-dimension and CTA-per-IVP instances keep the
+    // original order (the late order costs them registers: Brusselator N = 16 was 1.5x slower).
+    constexpr bool LATE_BLOCKS = (GROUP == 1 && !WIDE);
     // merge with the running conditional (A.4); running conditional lives in shared memory
     double Gm[N][N], gm[N][D], Lm[N][N];
+    auto merge_running_conditional = [&]() {
     if (FIX) {
       double G1[N][N];
 #pragma unroll
@@ -952,12 +959,45 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
 #pragma unroll
         for (int j = 0; j <= i; ++j) Lm[i][j] = Mt[j][i];
     }
+    };
+    if constexpr (!LATE_BLOCKS) merge_running_conditional();
     // correction (noise-free observation, sqrt form)
     double m_new[N][D], L_new[N][N];
     double gain[N];
     double e_norm;
+    double hL[Q + 1];
+    auto corrected_factor = [&]() {
+    // Mc[j][i] = L_ext[i][j] - hL[j] gain[i]; rows j > Q are untouched rows of L_ext^T
+    double Mc[Q + 1][N];
+#pragma unroll
+    for (int j = 0; j <= Q; ++j)
+#pragma unroll
+      for (int i = 0; i < N; ++i) Mc[j][i] = fma(-hL[j], gain[i], (j <= i) ? L_ext[i][j] : 0.0);
+#pragma unroll
+    for (int c0 = 0; c0 < Q; ++c0) {
+      double sigma2 = 0.0;
+#pragma unroll
+      for (int i = c0 + 1; i <= Q; ++i) sigma2 = fma(Mc[i][c0], Mc[i][c0], sigma2);
+      Reflector rf = make_reflector(Mc[c0][c0], sigma2);
+#pragma unroll
+      for (int c = c0 + 1; c < N; ++c) {
+        double w = 0.0;
+#pragma unroll
+        for (int i = c0 + 1; i <= Q; ++i) w = fma(Mc[i][c0], Mc[i][c], w);
+        w = fma(rf.v0, Mc[c0][c], w);
+        double f = w * rf.g;
+        Mc[c0][c] = fma(-f, rf.v0, Mc[c0][c]);
+#pragma unroll
+        for (int i = c0 + 1; i <= Q; ++i) Mc[i][c] = fma(-f, Mc[i][c0], Mc[i][c]);
+      }
+      Mc[c0][c0] = rf.beta;
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int j = 0; j <= i; ++j) L_new[i][j] = (j <= Q) ? Mc[j][i] : L_ext[i][j];
+    };
     {
-      double hL[Q + 1];
       double S = 0.0;
 #pragma unroll
       for (int j = 0; j <= Q; ++j) {
@@ -975,35 +1015,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
         for (int j = 0; j <= ((i < Q) ? i : Q); ++j) acc = fma(L_ext[i][j], hL[j], acc);
         gain[i] = acc * invS;
       }
-      // Mc[j][i] = L_ext[i][j] - hL[j] gain[i]; rows j > Q are untouched rows of L_ext^T
-      double Mc[Q + 1][N];
-#pragma unroll
-      for (int j = 0; j <= Q; ++j)
-#pragma unroll
-        for (int i = 0; i < N; ++i) Mc[j][i] = fma(-hL[j], gain[i], (j <= i) ? L_ext[i][j] : 0.0);
-#pragma unroll
-      for (int c0 = 0; c0 < Q; ++c0) {
-        double sigma2 = 0.0;
-#pragma unroll
-        for (int i = c0 + 1; i <= Q; ++i) sigma2 = fma(Mc[i][c0], Mc[i][c0], sigma2);
-        Reflector rf = make_reflector(Mc[c0][c0], sigma2);
-#pragma unroll
-        for (int c = c0 + 1; c < N; ++c) {
-          double w = 0.0;
-#pragma unroll
-          for (int i = c0 + 1; i <= Q; ++i) w = fma(Mc[i][c0], Mc[i][c], w);
-          w = fma(rf.v0, Mc[c0][c], w);
-          double f = w * rf.g;
-          Mc[c0][c] = fma(-f, rf.v0, Mc[c0][c]);
-#pragma unroll
-          for (int i = c0 + 1; i <= Q; ++i) Mc[i][c] = fma(-f, Mc[i][c0], Mc[i][c]);
-        }
-        Mc[c0][c0] = rf.beta;
-      }
-#pragma unroll
-      for (int i = 0; i < N; ++i)
-#pragma unroll
-        for (int j = 0; j <= i; ++j) L_new[i][j] = (j <= Q) ? Mc[j][i] : L_ext[i][j];
+      if constexpr (!LATE_BLOCKS) corrected_factor();
 #pragma unroll
       for (int i = 0; i < N; ++i)
 #pragma unroll
@@ -1041,6 +1053,10 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
       fac = (e_norm != e_norm) ? e_norm : fac;
       fac = (fac < a.factor_max) ? fac : a.factor_max;
       fac = (fac > a.factor_min) ? fac : a.factor_min;
+    }
+    if constexpr (LATE_BLOCKS) {
+      corrected_factor();
+      merge_running_conditional();
     }
     // ==================== per-lane bookkeeping (cheap, may diverge) =====================
     // helpers -------------------------------------------------------------------------
