@@ -52,7 +52,7 @@ W_SWEEP_PER_K = 5.33 * N_**3 + 2 * N_**2 * D_       # one backward marginalisati
 # DRAM traffic of one solver-kernel launch on the headline workload (ncu, profiles/r01_scalar_kernel_final_ncu.txt):
 # 0.213 GB read + 1.286 GB written = the checkpoint conditionals of the fixed-point smoother
 # (65,536 members x 49 checkpoints x 65 doubles = 1.67 GB, part of it still in L2 at kernel end).
-NCU_DRAM_BYTES_PER_LAUNCH = 314.720256e6 + 1.402810e9  # read + write, profiles/r01_scalar_kernel_final_ncu.txt
+NCU_DRAM_BYTES_PER_LAUNCH = 312.109056e6 + 1.402017e9  # read + write, profiles/r01_scalar_kernel_final_ncu.txt
 
 
 def ensemble_inputs(first, count, stride=1):
