@@ -630,6 +630,12 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
       continue;
     }
     stat_warp_iters += 1;
+    if constexpr (SLICE) {
+      // belt and braces: every warp re-derives the queue mask from the counters once in a while, so a
+      // parked member could not stay invisible even if no warp ever ran completely out of work
+      if ((stat_warp_iters & 4095ULL) == 0 && (threadIdx.x & 31) == 0)
+        slice_repair(&a, (int)((a.K - 2) >> a.slice_shift) + 1);
+    }
     stat_lane_iters += __popc(active);
     stat_interp_iters += __popc(__ballot_sync(0xffffffffu, have && mode != MODE_STEP));
     if (!have) continue;  // idle lane
