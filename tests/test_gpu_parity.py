@@ -224,13 +224,15 @@ GROUP_CASES = [
     ("pleiades", 14, 4, 2, 0, (), pu.pleiades_u0, np.linspace(0, 3, 50), 16, dict(atol=1e-8, rtol=1e-5, dt0=0.1, fact="blockdiag")),
     ("pleiades", 14, 5, 2, 0, (), pu.pleiades_u0, np.linspace(0, 3, 50), 16, dict(atol=1e-9, rtol=1e-6, dt0=0.1, fact="blockdiag", calib="none")),
     ("pleiades", 14, 8, 2, 0, (), pu.pleiades_u0, np.linspace(0, 3, 20), 16, dict(atol=1e-10, rtol=1e-7, dt0=0.1, fact="blockdiag")),
+    ("pleiades", 14, 3, 2, 0, (), pu.pleiades_u0, np.linspace(0, 3, 20), 16, dict(atol=1e-7, rtol=1e-4, dt0=0.1, fact="isotropic", strat="filter")),
+    ("pleiades", 14, 5, 2, 0, (), pu.pleiades_u0, np.linspace(0, 3, 20), 16, dict(atol=1e-9, rtol=1e-6, dt0=0.1, fact="isotropic", strat="filter")),
     ("rigid_body", 3, 4, 1, 3, pu.RIGID_BODY_PARAMS, pu.rigid_body_u0, np.linspace(0, 50, 5), 4, dict(atol=1e-9, rtol=1e-6, dt0=50.0, fact="blockdiag")),
     ("three_body", 2, 4, 2, 1, (pu.THREE_BODY_MU,), pu.three_body_u0, np.linspace(0, pu.THREE_BODY_T, 50), 2, dict(atol=1e-7, rtol=1e-7, fact="blockdiag")),
     ("lotka_volterra", 2, 4, 1, 4, (0.5, 0.05, 0.5, 0.05), lambda: np.array([[20.0, 20.0]]), np.linspace(0, 20, 30), 2, dict(atol=1e-6, rtol=1e-6, dt0=0.1, fact="blockdiag")),
 ]
 
 
-@pytest.mark.parametrize("case", GROUP_CASES, ids=lambda c: f"{c[0]}-nu{c[2]}-{c[9]['fact']}")
+@pytest.mark.parametrize("case", GROUP_CASES, ids=lambda c: f"{c[0]}-nu{c[2]}-{c[9]['fact']}-{c[9].get('strat', 'fixedpoint')}")
 def test_lane_per_dimension_kernels_bitwise_vs_oracle(cabi, oracle, case):
     problem, d, nu, q, P, params, u0fn, save_at, group, kw = case
     kw = dict(kw, P=P)
