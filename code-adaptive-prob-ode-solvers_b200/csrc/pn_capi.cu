@@ -76,6 +76,7 @@ struct Plan {
   size_t ws_ticket = 256;  // header: work-queue ticket + stats (256 B), ordering histogram / cursors, order[B]
   size_t ws_cond = 0;      // bytes of conditionals
   size_t ws_wide = 0;      // wide kernels: per-member mean arrays
+  int wide_smem_means = 0;  // wide kernels: how many mean arrays of the running member live in shared memory
   size_t ws_slice = 0;     // time-sliced scheduling: ready queues [G][B] + control words + parked states [B][ctx]
   int slice_shift = 0;     // queue group of a member = (k_next - 1) >> slice_shift, G <= 63 groups
   size_t ws_queue = 0;     // ... of which the ready queues (set to -1 before every launch)
@@ -90,6 +91,8 @@ struct Plan {
 // ---------------------------------------------------------------------------------------
 // control block of the time-sliced scheduler: sw[2] (queue mask, finished members) + 64 (pop, push) pairs
 constexpr size_t SLICE_CONTROL_BYTES = 1024;
+constexpr long long WIDE_SMEM_MAX_MEMBERS = 148;       // SMs of a B200: one CTA-per-IVP member per SM
+constexpr size_t WIDE_SMEM_LIMIT_BYTES = 227 * 1024;   // dynamic shared memory per CTA on sm_100
 constexpr int SLICE_MIN_CHECKPOINTS = 8;
 constexpr size_t SLICE_MAX_QUEUE_BYTES = (size_t)512 << 20;
 constexpr int ORDER_BUCKETS = 128;
@@ -176,7 +179,17 @@ static int make_plan(const pn_b200_desc* d, Plan* p, bool need_device) {
   p->smem = family_is_dense(p->k->family)
                 ? (size_t)p->k->smem_doubles * (p->k->threads / 32) * sizeof(double)  // per warp
                 : (size_t)p->k->smem_doubles * p->k->threads * sizeof(double);        // per thread
-  if (p->k->family == FAMILY_WIDE) p->smem += ((size_t)2 * d->d + p->k->threads / 32 + 2) * sizeof(double);
+  if (p->k->family == FAMILY_WIDE) {
+    p->smem += ((size_t)2 * d->d + p->k->threads / 32 + 2) * sizeof(double);
+    // few members (at most one per SM: no occupancy to lose) whose mean arrays fit next to the rest
+    const size_t one = (size_t)(d->nu + 1) * d->d * sizeof(double);
+    if (d->batch <= WIDE_SMEM_MAX_MEMBERS && !getenv("PN_B200_WIDE_GLOBAL_MEANS")) {
+      while (p->wide_smem_means < 3 && p->smem + one <= WIDE_SMEM_LIMIT_BYTES) {
+        p->smem += one;
+        p->wide_smem_means += 1;
+      }
+    }
+  }
   p->ws_ticket = (WS_ORDER_OFFSET + (size_t)d->batch * sizeof(long long) + 255) / 256 * 256;
   p->ws_cond = (size_t)d->num_save_at * p->k->slot_doubles * (size_t)d->batch * p->k->dv * sizeof(double);
   if (p->k->family == FAMILY_WIDE) {
@@ -345,6 +358,7 @@ int pn_b200_solve_save_at(const pn_b200_desc* desc, const double* u0, const doub
   a.ticket = (unsigned long long*)workspace;
   a.cond = (double*)((char*)workspace + p.ws_ticket);
   a.wide_d = (p.k->family == FAMILY_WIDE) ? desc->d : 0;
+  a.wide_smem_means = p.wide_smem_means;
   a.wide_mean = (double*)((char*)workspace + p.ws_ticket + p.ws_cond);
   a.out_scale = output_scale;
   a.n_accepted = (long long*)n_accepted;

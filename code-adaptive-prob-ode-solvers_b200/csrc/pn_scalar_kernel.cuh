@@ -105,6 +105,8 @@ struct SolveArgs {
   // wide (CTA-per-IVP) kernel only: runtime ODE dimension and the per-member mean arrays
   // [B][3][n][d] (state mean, backward-conditional offset g, pending mean) in global memory
   int wide_d;
+  int wide_smem_means;  // how many of the member's mean arrays (state mean, conditional offset g, pending mean -- in
+                        // that order) live in shared memory instead of wide_mean: few members, as many as fit
   double* wide_mean;
   // Prior constant: lower Cholesky factor of the flipped Hilbert matrix, row-major
   // n x n, computed by the host (pn_capi.cu).  Kernel parameters live in the constant bank, so
@@ -411,6 +413,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
   double* s_ubuf = smem + ((FIX ? Lay::BW : 0) + Lay::PEND + Lay::MARG) * THREADS;  // [d] predicted u
   double* s_zbuf = s_ubuf + wd;                                                      // [d] residual z
   double* s_red = s_zbuf + wd;                                                       // [THREADS/32]
+  double* s_means = s_red + THREADS / 32 + 2;                                        // [3][n][d] if wide_smem_means
   double* Wm = nullptr;    // state mean [n][d]
   double* Wg = nullptr;    // backward-conditional offset g [n][d]
   double* Wp = nullptr;    // pending (accepted, uncommitted) mean [n][d]
@@ -494,9 +497,14 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
         sigma0 = a.sigma0 ? a.sigma0[b] : 1.0;
         if (!resume) {
         if constexpr (WIDE) {
+          // state mean, backward-conditional offset and pending mean: shared memory when the launch has at
+          // most one member per SM and they fit (each pass over the columns then saves an L2 round trip)
           Wm = a.wide_mean + (size_t)b * 3 * N * wd;
           Wg = Wm + (size_t)N * wd;
           Wp = Wg + (size_t)N * wd;
+          if (a.wide_smem_means > 0) Wm = s_means;
+          if (a.wide_smem_means > 1) Wg = s_means + (size_t)N * wd;
+          if (a.wide_smem_means > 2) Wp = s_means + (size_t)2 * N * wd;
           wcond = a.cond + (size_t)b * a.K * wslot;
           // Taylor-mode initialisation of the Brusselator, one grid point per thread and order
           // (normalised coefficients C_k in Wm; the k-th coefficient of f only needs C_0..C_k)

@@ -386,6 +386,24 @@ def test_wide_brusselator_bitwise_vs_oracle(cabi, oracle, goldens, N, K, tol):
         np.testing.assert_allclose(gpu["u"][0], goldens["brusselator_ys_N32"], rtol=0, atol=5e-8)
 
 
+def test_wide_brusselator_ensemble_beyond_one_member_per_sm(cabi, oracle):
+    # up to 148 members the running member's mean arrays live in shared memory; beyond, in the per-member
+    # global arrays (two CTAs per SM).  Same bits either way.
+    N, B, K = 20, 200, 6
+    rng = np.random.default_rng(5)
+    alpha = (1.0 / 50.0) * 10.0 ** rng.uniform(-0.5, 0.5, B)
+    u0 = np.tile(pu.brusselator_u0(N)[None], (B, 1, 1))
+    save_at = np.linspace(0.0, 2.0, K)
+    kw = dict(atol=1e-6, rtol=1e-6, dt0=0.01, P=1)
+    many = cabi.solve_host(_desc(cabi, "brusselator", 2 * N, 4, 1, B, K, **kw), u0, alpha[:, None], None, save_at, None)
+    few = cabi.solve_host(_desc(cabi, "brusselator", 2 * N, 4, 1, 100, K, **kw), u0[:100], alpha[:100, None], None, save_at, None)
+    for key in ("u", "u_std", "n_accepted", "n_rejected", "status"):
+        np.testing.assert_array_equal(many[key][:100], few[key])
+    idx = [0, 99, 150, 199]
+    ora = oracle.solve_save_at_batch(_ocfg(oracle, "brusselator", 2 * N, 4, 1, reduction_group=128, **kw), u0[idx], alpha[idx, None], save_at)
+    _assert_bitwise({k: v[idx] for k, v in many.items()}, ora)
+
+
 def test_wide_brusselator_terminal_values_and_filter(cabi, oracle):
     # solve_adaptive_terminal_values (run.py:82-90) = two checkpoints; also the filter strategy
     N = 24
