@@ -68,6 +68,31 @@ struct Geometry {
 };
 static std::vector<Geometry> g_geom;
 static std::mutex g_geom_mutex;
+// Largest dynamic shared memory size a kernel's attribute has been raised to, per (device, kernel).  The
+// attribute is ONE value per function: it is only ever raised, never set back to a smaller request (a
+// kernel is launched with different sizes: the CTA-per-IVP kernels stage 2 d doubles and, for few
+// members, their mean arrays).
+struct SmemLimit {
+  int dev;
+  const void* func;
+  size_t bytes;
+};
+static std::vector<SmemLimit> g_smem_limit;
+
+static cudaError_t raise_smem_limit(int dev, const void* func, size_t bytes) {
+  if (!func) return cudaSuccess;
+  std::lock_guard<std::mutex> lock(g_geom_mutex);
+  for (auto& l : g_smem_limit)
+    if (l.dev == dev && l.func == func) {
+      if (bytes <= l.bytes) return cudaSuccess;
+      cudaError_t ce = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+      if (ce == cudaSuccess) l.bytes = bytes;
+      return ce;
+    }
+  cudaError_t ce = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (ce == cudaSuccess) g_smem_limit.push_back({dev, func, bytes});
+  return ce;
+}
 
 struct Plan {
   const KernelEntry* k = nullptr;
@@ -227,9 +252,8 @@ static int make_plan(const pn_b200_desc* d, Plan* p, bool need_device) {
   if (p->ctas_per_sm == 0) {
     ce = cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, cudaGetErrorString(ce));
-    ce = cudaFuncSetAttribute(p->k->solve_func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
-    if (ce == cudaSuccess && p->k->solve_func_sliced)
-      ce = cudaFuncSetAttribute(p->k->solve_func_sliced, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
+    ce = raise_smem_limit(dev, p->k->solve_func, p->smem);
+    if (ce == cudaSuccess) ce = raise_smem_limit(dev, p->k->solve_func_sliced, p->smem);
     if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce));
     int occ = 0;
     ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, p->k->solve_func, p->k->threads, p->smem);

@@ -404,6 +404,25 @@ def test_wide_brusselator_ensemble_beyond_one_member_per_sm(cabi, oracle):
     _assert_bitwise({k: v[idx] for k, v in many.items()}, ora)
 
 
+def test_wide_kernel_shared_memory_sizes_in_any_order(cabi):
+    # one kernel, launched with different dynamic shared-memory sizes (2 d staging doubles + mean arrays):
+    # large -> small -> large must work (the function attribute is only ever raised)
+    save_at = np.linspace(0.0, 0.5, 4)
+    kw = dict(atol=1e-5, rtol=1e-5, dt0=0.01, P=1)
+
+    def run(N, B):
+        u0 = np.tile(pu.brusselator_u0(N)[None], (B, 1, 1))
+        return cabi.solve_host(_desc(cabi, "brusselator", 2 * N, 4, 1, B, 4, **kw), u0, np.full((B, 1), 0.02), None, save_at, None)
+
+    first = run(100, 2)
+    run(20, 2)
+    run(20, 160)
+    again = run(100, 2)
+    assert (again["status"] == 0).all()
+    np.testing.assert_array_equal(first["u"], again["u"])
+    np.testing.assert_array_equal(first["n_accepted"], again["n_accepted"])
+
+
 def test_wide_brusselator_terminal_values_and_filter(cabi, oracle):
     # solve_adaptive_terminal_values (run.py:82-90) = two checkpoints; also the filter strategy
     N = 24
