@@ -325,6 +325,8 @@ def main():
                 "members_total": B_total, "parallelism": f"ensemble sharded x{world}, one all-gather of results" if world > 1 else "single GPU",
                 "l2": "256 MiB device memset between timed steps (L2 flush)",
                 "kernel": info,
+                "scheduling": ("run to completion (PN_B200_NO_SLICE)" if os.environ.get("PN_B200_NO_SLICE")
+                               else "time-sliced members: parked at quantum boundaries, most lagging ready member first"),
             },
             "gpu_launches": 2 * args.steps,
             "e2e": {"value": B_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
