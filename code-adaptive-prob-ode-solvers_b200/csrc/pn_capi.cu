@@ -56,9 +56,12 @@ static void prior_lq(int nu, double* lq /* n*n row-major */) {
 }
 
 // optional kernel timing (pn_b200_set_profiling)
-static bool g_profiling = false;
-static cudaEvent_t g_ev[4];
-static bool g_ev_ready = false, g_ev_recorded = false;
+// State is per calling thread (the report that asked for timing reads its own events back) and the
+// events are re-created when the thread moves to another device.
+static thread_local bool g_profiling = false;
+static thread_local cudaEvent_t g_ev[4];
+static thread_local int g_ev_dev = -1;
+static thread_local bool g_ev_recorded = false;
 
 struct Geometry {
   int dev;
@@ -92,6 +95,30 @@ static cudaError_t raise_smem_limit(int dev, const void* func, size_t bytes) {
   cudaError_t ce = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   if (ce == cudaSuccess) g_smem_limit.push_back({dev, func, bytes});
   return ce;
+}
+
+// private memory pool of the host entry point, one per device
+struct HostPool {
+  int dev;
+  cudaMemPool_t pool;
+};
+static std::vector<HostPool> g_host_pools;
+static cudaMemPool_t host_pool(int dev) {
+  std::lock_guard<std::mutex> lock(g_geom_mutex);
+  for (auto& hp : g_host_pools)
+    if (hp.dev == dev) return hp.pool;
+  cudaMemPoolProps props;
+  memset(&props, 0, sizeof props);
+  props.allocType = cudaMemAllocationTypePinned;
+  props.handleTypes = cudaMemHandleTypeNone;
+  props.location.type = cudaMemLocationTypeDevice;
+  props.location.id = dev;
+  cudaMemPool_t pool = nullptr;
+  if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) return nullptr;
+  unsigned long long keep = ~0ULL;
+  cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  g_host_pools.push_back({dev, pool});
+  return pool;
 }
 
 struct Plan {
@@ -319,6 +346,31 @@ size_t pn_b200_workspace_bytes(const pn_b200_desc* desc) {
   return p.ws_ticket + p.ws_cond + p.ws_wide + p.ws_slice;
 }
 
+int pn_b200_output_sizes(const pn_b200_desc* desc, pn_b200_sizes* sz) {
+  const KernelEntry* k = nullptr;
+  int rc = resolve(desc, &k);
+  if (rc) return rc;
+  if (!sz) return fail(PN_B200_ERR_ARGUMENT, "null sizes");
+  const size_t B = (size_t)desc->batch, K = (size_t)desc->num_save_at, d = (size_t)desc->d, n = (size_t)desc->nu + 1;
+  const bool bdiag = desc->factorisation == PN_B200_BLOCKDIAG && d > 1;
+  const bool dense = desc->factorisation == PN_B200_DENSE && d > 1;
+  const bool rec = (desc->flags & PN_B200_FLAG_RECORD) != 0;
+  const size_t cap = rec ? (size_t)desc->traj_capacity : 0;
+  memset(sz, 0, sizeof *sz);
+  sz->u = sz->u_std = B * K * d;
+  sz->marg_mean = B * K * n * d;
+  sz->marg_chol = B * K * (bdiag ? d : (dense ? d * d : 1)) * n * n;
+  sz->output_scale = B * K * (bdiag ? d : 1);
+  sz->n_accepted = B * K;
+  sz->n_rejected = B;
+  sz->status = B;
+  sz->traj_t = cap * B;
+  sz->traj_u = cap * d * B;
+  sz->traj_std = cap * B;
+  sz->traj_len = rec ? B : 0;
+  return PN_B200_SUCCESS;
+}
+
 int pn_b200_get_kernel_info(const pn_b200_desc* desc, pn_b200_kernel_info* info) {
   Plan p;
   int rc = make_plan(desc, &p, true);
@@ -431,9 +483,16 @@ int pn_b200_solve_save_at(const pn_b200_desc* desc, const double* u0, const doub
     a.ctx = (double*)(base + p.ws_queue + SLICE_CONTROL_BYTES);
   }
   const bool prof = g_profiling;
-  if (prof && !g_ev_ready) {
-    for (auto& e : g_ev) cudaEventCreate(&e);
-    g_ev_ready = true;
+  if (prof) {
+    int dev_now = 0;
+    cudaGetDevice(&dev_now);
+    if (g_ev_dev != dev_now) {
+      if (g_ev_dev >= 0)
+        for (auto& e : g_ev) cudaEventDestroy(e);
+      for (auto& e : g_ev) cudaEventCreate(&e);
+      g_ev_dev = dev_now;
+      g_ev_recorded = false;
+    }
   }
   if (prof) cudaEventRecord(g_ev[0], stream);
   ce = sliced ? p.k->launch_solve_sliced(a, p.grid, p.smem, stream) : p.k->launch_solve(a, p.grid, p.smem, stream);
@@ -545,16 +604,21 @@ int pn_b200_solve_save_at_host(const pn_b200_desc* desc, const double* u0, const
                                double* u, double* u_std, double* marg_mean, double* marg_chol,
                                double* output_scale, int64_t* n_accepted, int64_t* n_rejected, int32_t* status, double* traj_t,
                                double* traj_u, double* traj_std, int64_t* traj_len, int device) {
-  cudaError_t ce = cudaSetDevice(device);
-  if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, cudaGetErrorString(ce));
-  const KernelEntry* k = nullptr;
-  int rc = resolve(desc, &k);
+  pn_b200_sizes sz;
+  int rc = pn_b200_output_sizes(desc, &sz);
   if (rc) return rc;
   if (desc->batch == 0) return PN_B200_SUCCESS;
-  const size_t B = (size_t)desc->batch, K = (size_t)desc->num_save_at, d = (size_t)desc->d, n = (size_t)desc->nu + 1;
+  // the caller's current device is restored on every exit path
+  struct DeviceGuard {
+    int prev = -1;
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  } guard;
+  cudaError_t ce = cudaGetDevice(&guard.prev);
+  if (ce != cudaSuccess) guard.prev = -1;
+  ce = cudaSetDevice(device);
+  if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, cudaGetErrorString(ce));
+  const size_t B = (size_t)desc->batch, K = (size_t)desc->num_save_at, d = (size_t)desc->d;
   const size_t q = (size_t)desc->ode_order, P = (size_t)desc->num_params;
-  const bool rec = (desc->flags & PN_B200_FLAG_RECORD) != 0;
-  const size_t cap = rec ? (size_t)desc->traj_capacity : 0;
   struct Buf {
     void** dev;
     const void* host_in;
@@ -571,37 +635,32 @@ int pn_b200_solve_save_at_host(const pn_b200_desc* desc, const double* u0, const
       {&d_tol, tol, nullptr, tol ? B * 2 * 8 : 0},
       {&d_save, save_at, nullptr, K * 8},
       {&d_os, output_scale0, nullptr, output_scale0 ? B * 8 : 0},
-      {&d_u, nullptr, u, B * K * d * 8},
-      {&d_std, nullptr, u_std, B * K * d * 8},
-      {&d_mm, nullptr, marg_mean, marg_mean ? B * K * n * d * 8 : 0},
-      {&d_mc, nullptr, marg_chol,
-       marg_chol ? B * K * (k->family == FAMILY_GROUP_BDIAG ? d : (family_is_dense(k->family) ? d * d : 1)) * n * n * 8 : 0},
-      {&d_sc, nullptr, output_scale, output_scale ? B * K * (k->family == FAMILY_GROUP_BDIAG ? d : 1) * 8 : 0},
-      {&d_nacc, nullptr, n_accepted, B * K * 8},
-      {&d_nrej, nullptr, n_rejected, B * 8},
-      {&d_stat, nullptr, status, B * 4},
-      {&d_tt, nullptr, traj_t, rec ? cap * B * 8 : 0},
-      {&d_tu, nullptr, traj_u, rec ? cap * d * B * 8 : 0},
-      {&d_ts, nullptr, traj_std, rec ? cap * B * 8 : 0},
-      {&d_tl, nullptr, traj_len, rec ? B * 8 : 0},
+      {&d_u, nullptr, u, sz.u * 8},
+      {&d_std, nullptr, u_std, sz.u_std * 8},
+      {&d_mm, nullptr, marg_mean, marg_mean ? sz.marg_mean * 8 : 0},
+      {&d_mc, nullptr, marg_chol, marg_chol ? sz.marg_chol * 8 : 0},
+      {&d_sc, nullptr, output_scale, output_scale ? sz.output_scale * 8 : 0},
+      {&d_nacc, nullptr, n_accepted, sz.n_accepted * 8},
+      {&d_nrej, nullptr, n_rejected, sz.n_rejected * 8},
+      {&d_stat, nullptr, status, sz.status * 4},
+      {&d_tt, nullptr, traj_t, sz.traj_t * 8},
+      {&d_tu, nullptr, traj_u, sz.traj_u * 8},
+      {&d_ts, nullptr, traj_std, sz.traj_std * 8},
+      {&d_tl, nullptr, traj_len, sz.traj_len * 8},
       {&d_ws, nullptr, nullptr, ws_bytes},
   };
-  // keep freed blocks in the stream-ordered pool between calls (the default releases them at every
-  // synchronisation, which would re-map the multi-GB workspace on each solve)
-  {
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-      unsigned long long keep = ~0ULL;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
-  }
+  // The host entry allocates from a PRIVATE stream-ordered pool per device (never the process's default
+  // pool, which other libraries share): freed blocks stay in it between calls, so the multi-GB workspace
+  // is not re-mapped on every solve, and pn_b200_trim() hands the memory back to the driver.
+  cudaMemPool_t pool = host_pool(device);
+  if (!pool) return fail(PN_B200_ERR_CUDA, "cannot create the host entry point's memory pool");
   cudaStream_t stream;
   ce = cudaStreamCreate(&stream);
   if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, cudaGetErrorString(ce));
   rc = PN_B200_SUCCESS;
   for (auto& bf : bufs) {
     if (!bf.bytes) continue;
-    ce = cudaMallocAsync(bf.dev, bf.bytes, stream);
+    ce = cudaMallocFromPoolAsync(bf.dev, bf.bytes, pool, stream);
     if (ce != cudaSuccess) { rc = fail(PN_B200_ERR_CUDA, std::string("cudaMallocAsync: ") + cudaGetErrorString(ce)); break; }
     if (bf.host_in) {
       ce = cudaMemcpyAsync(*bf.dev, bf.host_in, bf.bytes, cudaMemcpyHostToDevice, stream);
@@ -628,6 +687,16 @@ int pn_b200_solve_save_at_host(const pn_b200_desc* desc, const double* u0, const
   cudaStreamSynchronize(stream);
   cudaStreamDestroy(stream);
   return rc;
+}
+
+int pn_b200_trim(int device) {
+  std::lock_guard<std::mutex> lock(g_geom_mutex);
+  for (auto& hp : g_host_pools)
+    if (hp.dev == device) {
+      cudaError_t ce = cudaMemPoolTrimTo(hp.pool, 0);
+      return ce == cudaSuccess ? PN_B200_SUCCESS : fail(PN_B200_ERR_CUDA, cudaGetErrorString(ce));
+    }
+  return PN_B200_SUCCESS;
 }
 
 // Test hook (not part of the public header): evaluates the kernels' branch-free rcp / sqrt / pow.

@@ -74,9 +74,19 @@ class KernelInfo(C.Structure):
     ]
 
 
+class Sizes(C.Structure):
+    """pn_b200_sizes"""
+
+    _fields_ = [(name, C.c_size_t) for name in (
+        "u", "u_std", "marg_mean", "marg_chol", "output_scale", "n_accepted", "n_rejected", "status",
+        "traj_t", "traj_u", "traj_std", "traj_len")]  # fmt: skip
+
+
 EXPORTS = (
     "pn_b200_supported",
     "pn_b200_workspace_bytes",
+    "pn_b200_output_sizes",
+    "pn_b200_trim",
     "pn_b200_solve_save_at",
     "pn_b200_solve_save_at_host",
     "pn_b200_get_kernel_info",
@@ -110,6 +120,10 @@ def lib():
         L.pn_b200_supported.argtypes = [C.POINTER(Desc)]
         L.pn_b200_workspace_bytes.restype = C.c_size_t
         L.pn_b200_workspace_bytes.argtypes = [C.POINTER(Desc)]
+        L.pn_b200_output_sizes.restype = C.c_int
+        L.pn_b200_output_sizes.argtypes = [C.POINTER(Desc), C.POINTER(Sizes)]
+        L.pn_b200_trim.restype = C.c_int
+        L.pn_b200_trim.argtypes = [C.c_int]
         L.pn_b200_solve_save_at.restype = C.c_int
         L.pn_b200_solve_save_at.argtypes = [C.POINTER(Desc)] + [dp] * 17 + [vp, C.c_size_t, vp]
         L.pn_b200_solve_save_at_host.restype = C.c_int
@@ -153,6 +167,13 @@ def supported(desc):
 def workspace_bytes(desc):
     check(lib().pn_b200_supported(C.byref(desc)))
     return int(lib().pn_b200_workspace_bytes(C.byref(desc)))
+
+
+def output_sizes(desc):
+    """Element counts of every output buffer (pn_b200_output_sizes)."""
+    sz = Sizes()
+    check(lib().pn_b200_output_sizes(C.byref(desc), C.byref(sz)))
+    return {name: int(getattr(sz, name)) for name, _ in Sizes._fields_}
 
 
 def kernel_info(desc):

@@ -10,8 +10,12 @@
  * descriptor, a CUDA stream.  No torch/jax types.  See INTEGRATION.md for the binding stubs.
  *
  * Ownership: the caller owns every buffer.  `pn_b200_solve_save_at` takes DEVICE pointers, is
- * stream-ordered and asynchronous, keeps no global state besides immutable constant tables,
- * and is re-entrant across streams as long as each call has its own workspace.
+ * stream-ordered and asynchronous, and is re-entrant across streams and threads as long as each
+ * call has its own workspace.  Process-wide state is limited to immutable constant tables, a cache
+ * of launch geometry per (device, kernel), and -- for `pn_b200_solve_save_at_host` only -- one
+ * private stream-ordered memory pool per device that keeps its blocks between calls (release them
+ * with `pn_b200_trim`).  The host entry restores the caller's current device before it returns.
+ * The optional kernel timing (`pn_b200_set_profiling`) is per calling thread.
  * Per-member numerical failure never aborts the batch: it is reported in status[b].
  */
 #ifndef PN_B200_H
@@ -74,6 +78,18 @@ int pn_b200_supported(const pn_b200_desc* desc);
 /* Device scratch the solve needs (the K backward conditionals per member: O(K), not O(#steps)). */
 size_t pn_b200_workspace_bytes(const pn_b200_desc* desc);
 
+/* Element counts of every output buffer of pn_b200_solve_save_at for `desc` (doubles, except
+ * n_accepted / n_rejected / traj_len: int64 and status: int32).  Callers size their buffers from
+ * this instead of deriving shapes by hand (marg_chol depends on the factorisation, see below). */
+typedef struct {
+  size_t u, u_std;                 /* B*K*d each                                             */
+  size_t marg_mean, marg_chol;     /* optional outputs                                       */
+  size_t output_scale;             /* B*K, blockdiag: B*K*d                                  */
+  size_t n_accepted, n_rejected, status;
+  size_t traj_t, traj_u, traj_std, traj_len; /* 0 unless PN_B200_FLAG_RECORD                 */
+} pn_b200_sizes;
+int pn_b200_output_sizes(const pn_b200_desc* desc, pn_b200_sizes* sizes);
+
 /*
  * solve_adaptive_save_at + backward marginalisation for a whole ensemble (DEVICE pointers).
  *   u0            [B][q][d]     initial values (u, u', ...)
@@ -82,8 +98,13 @@ size_t pn_b200_workspace_bytes(const pn_b200_desc* desc);
  *   save_at       [K]           checkpoints, strictly increasing, save_at[0] = t0
  *   output_scale0 [B] | NULL    initial output scale (ivpsolvers.py:55,68); NULL: 1.0
  *   u, u_std      [B][K][d]     smoothed checkpoint means / marginal standard deviations
- *   marg_mean     [B][K][n][d] | NULL, marg_chol [B][K][n][n] | NULL   full marginals (n = nu+1);
- *                 blockdiag with d > 1: marg_chol is [B][K][d][n][n] (one factor per dimension)
+ *   marg_mean     [B][K][n][d] | NULL   full marginal means (n = nu+1; for the dense factorisation this
+ *                 is the flat state vector of length D = n*d, derivative-major index i*d + l)
+ *   marg_chol     | NULL                full marginal square-root factors, shape by factorisation:
+ *                 isotropic, and dense with d == 1:  [B][K][n][n]
+ *                 blockdiag with d > 1:              [B][K][d][n][n]   (one factor per dimension)
+ *                 dense with d > 1:                  [B][K][D][D], D = n*d, derivative-major
+ *                 -- size the buffer with pn_b200_output_sizes(), never by hand
  *   output_scale  [B][K] | NULL the output scale every checkpoint carries (solution.output_scale:
  *                 the calibrated sigma of the accepted step that reached or crossed it; entry 0 is
  *                 output_scale0); blockdiag: [B][K][d], one scale per dimension
@@ -109,6 +130,9 @@ int pn_b200_solve_save_at_host(const pn_b200_desc* desc, const double* u0, const
                                double* u, double* u_std, double* marg_mean, double* marg_chol,
                                double* output_scale, int64_t* n_accepted, int64_t* n_rejected, int32_t* status, double* traj_t,
                                double* traj_u, double* traj_std, int64_t* traj_len, int device);
+
+/* Returns the device memory cached by pn_b200_solve_save_at_host on `device` to the driver. */
+int pn_b200_trim(int device);
 
 /*
  * Joint samples from the checkpoint Markov sequence of a FINISHED fixed-point solve:

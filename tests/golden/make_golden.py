@@ -33,13 +33,27 @@ def _reconstruct_array(fun, args, arr_state, aval_state=None):
     return np.asarray(a)
 
 
+# /root/reference is untrusted public content: the pickles are decoded with an ALLOW-LIST of exactly
+# the globals a pickled numpy / jax array needs.  Anything else (os.system, builtins.eval, ...) raises.
+_ALLOWED_GLOBALS = {
+    ("numpy.core.multiarray", "_reconstruct"),
+    ("numpy._core.multiarray", "_reconstruct"),
+    ("numpy.core.multiarray", "scalar"),
+    ("numpy._core.multiarray", "scalar"),
+    ("numpy", "ndarray"),
+    ("numpy", "dtype"),
+}
+
+
 class _NoJaxUnpickler(pickle.Unpickler):
     def find_class(self, module, name):
         if module.split(".")[0] in ("jax", "jaxlib"):
             if name == "_reconstruct_array":
                 return _reconstruct_array
             raise pickle.UnpicklingError(f"unexpected jax global {module}.{name}")
-        return super().find_class(module, name)
+        if (module, name) in _ALLOWED_GLOBALS:
+            return super().find_class(module, name)
+        raise pickle.UnpicklingError(f"global {module}.{name} is not on the allow-list")
 
 
 def load_pickled_npy(path):
@@ -108,7 +122,7 @@ def main():
 
     # --- 5_vs_interpolation: three-body, isotropic EKF0 o2 nu=4 uncalibrated
     #     (measure.py:44-68,191-192): step counts at tol 1e-4/1e-7/1e-10
-    res = np.load(os.path.join(ex, "5_vs_interpolation", "data_results.npy"), allow_pickle=True).item()
+    res = load_pickled_npy(os.path.join(ex, "5_vs_interpolation", "data_results.npy"))
     steps = {}
     for row in res.values():
         steps[row["Tolerance"]] = int(row["No. steps"].replace(",", ""))
@@ -116,7 +130,7 @@ def main():
     out["threebody_num_steps"] = np.asarray(
         [steps["$10^{-4}$"], steps["$10^{-7}$"], steps["$10^{-10}$"]], dtype=np.int64
     )
-    sol = np.load(os.path.join(ex, "5_vs_interpolation", "data_solution.npy"), allow_pickle=True)
+    sol = np.load(os.path.join(ex, "5_vs_interpolation", "data_solution.npy"), allow_pickle=False)
     out["threebody_filter_solution"] = np.asarray(sol, dtype=np.float64)
 
     np.savez_compressed(OUT, **out)

@@ -39,6 +39,25 @@ def _worker(rank, world, port, B, K, d, q):
     ok = bool(torch.equal(out["u"][:, :, 0], member[:, None] * 10 + torch.arange(K, dtype=torch.float64)[None, :]))
     ok &= bool(torch.equal(out["n_accepted"], (torch.arange(B)[:, None] * 100 + torch.arange(K)[None, :])))
     ok &= bool(torch.equal(out["status"], (torch.arange(B) % 3).to(torch.int32)))
+    # the packed path: results are written into views of ONE buffer, one collective, strided member-order views
+    packed = ensemble.PackedResults(B, K, d, world, torch.device("cpu"))
+    mine = packed.local(len(idx))
+    mine["u"].copy_(local["u"])
+    mine["u_std"].copy_(local["u"] * 0.5)
+    mine["n_accepted"].copy_(local["n_accepted"])
+    mine["n_rejected"].copy_(torch.as_tensor(idx) * 7)
+    mine["status"].copy_(local["status"])
+    g = packed.all_gather()
+    for i in range(packed.capacity):
+        for r in range(world):
+            b = i * world + r
+            if b >= B:
+                continue
+            ok &= bool(g["u"][i, r, 0, 0].item() == b * 10) and bool(g["u_std"][i, r, K - 1, d - 1].item() == 0.5 * (b * 10 + K - 1))
+            ok &= bool(g["n_accepted"][i, r, 1].item() == b * 100 + 1) and bool(g["n_rejected"][i, r].item() == 7 * b)
+            ok &= bool(g["status"][i, r].item() == b % 3)
+    ok &= bool(torch.equal(packed.member_order(g["n_rejected"]), torch.arange(B) * 7))
+    ok &= g["u"].data_ptr() == packed._gathered.data_ptr()  # a view of the gathered buffer, not a copy
     t = torch.tensor([1.0 if ok else 0.0])
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
