@@ -176,6 +176,12 @@ __global__ void pn_order_scatter_kernel(const double* tol, long long B, unsigned
   if (i < B) order[atomicAdd(&cursor[order_bucket(tol[2 * i], tol[2 * i + 1])], 1u)] = i;
 }
 
+constexpr long long DENSE_CTA_MAX_CTAS = 148;  // per-CTA scratch regions the workspace provides (SMs of a B200)
+static size_t dense_cta_smem_bytes(const KernelEntry* k, const pn_b200_desc* d) {
+  const int Dn = (d->nu + 1) * d->d;
+  return (k->smem_doubles == 32 ? cta::smem_doubles<32>(Dn) : cta::smem_doubles<16>(Dn)) * sizeof(double);
+}
+
 static int resolve(const pn_b200_desc* d, const KernelEntry** out) {
   if (!d) return fail(PN_B200_ERR_ARGUMENT, "null descriptor");
   if (d->batch < 0 || d->num_save_at < 2) return fail(PN_B200_ERR_ARGUMENT, "need batch >= 0 and at least 2 save_at points");
@@ -206,6 +212,12 @@ static int resolve(const pn_b200_desc* d, const KernelEntry** out) {
     if (!(force && force[0] == '1')) k = find_kernel(FAMILY_DENSE_ROWS, d->problem, d->nu, d->strategy, d->d);
     if (!k) k = find_kernel(FAMILY_DENSE, d->problem, d->nu, d->strategy, d->d);
   }
+  // CTA-per-IVP dense family: dense factorisation with a large runtime dimension (Brusselator N >= 5:
+  // D = (nu+1) 2N > 40), blocked QR + DMMA products
+  if (!k && d->factorisation == PN_B200_DENSE && d->d > 1 && (d->d % 2) == 0) {
+    k = find_kernel(FAMILY_DENSE_CTA, d->problem, d->nu, d->strategy, 0);
+    if (k && dense_cta_smem_bytes(k, d) > WIDE_SMEM_LIMIT_BYTES) k = nullptr;  // D too large for one CTA's panel
+  }
   // CTA-per-IVP wide family: isotropic EKF0 with a runtime dimension (Brusselator beyond the fixed sizes)
   if (!k && d->correction == PN_B200_TS0 && d->factorisation == PN_B200_ISOTROPIC && d->d >= 4 && d->d <= 4096 &&
       (d->d % 2) == 0)
@@ -231,6 +243,7 @@ static int make_plan(const pn_b200_desc* d, Plan* p, bool need_device) {
   p->smem = family_is_dense(p->k->family)
                 ? (size_t)p->k->smem_doubles * (p->k->threads / 32) * sizeof(double)  // per warp
                 : (size_t)p->k->smem_doubles * p->k->threads * sizeof(double);        // per thread
+  if (p->k->family == FAMILY_DENSE_CTA) p->smem = dense_cta_smem_bytes(p->k, d);
   if (p->k->family == FAMILY_WIDE) {
     p->smem += ((size_t)2 * d->d + p->k->threads / 32 + 2) * sizeof(double);
     // few members (at most one per SM: no occupancy to lose) whose mean arrays fit next to the rest
@@ -248,6 +261,12 @@ static int make_plan(const pn_b200_desc* d, Plan* p, bool need_device) {
     const size_t nd = (size_t)(d->nu + 1) * d->d;
     p->ws_cond = (size_t)d->batch * ((size_t)d->num_save_at * (p->k->slot_doubles + 2 * nd)) * sizeof(double);
     p->ws_wide = (size_t)d->batch * 3 * nd * sizeof(double);
+  }
+  if (p->k->family == FAMILY_DENSE_CTA) {
+    const int Dn = (d->nu + 1) * d->d;
+    const long long ctas = d->batch < DENSE_CTA_MAX_CTAS ? d->batch : DENSE_CTA_MAX_CTAS;
+    p->ws_cond = (size_t)d->batch * d->num_save_at * cta::slot_doubles(Dn, d->strategy == PN_B200_FIXEDPOINT) * sizeof(double);
+    p->ws_wide = (size_t)ctas * cta::scratch_doubles(Dn, d->d, d->ode_order) * sizeof(double);
   }
   // time-sliced scheduling (pn_scalar_kernel.cuh: SolveArgs::slice): thread-per-IVP kernels, enough
   // checkpoints to slice at, bounded queue memory
@@ -294,6 +313,7 @@ static int make_plan(const pn_b200_desc* d, Plan* p, bool need_device) {
   const long long per_cta = (p->k->family == FAMILY_WIDE) ? 1 : p->k->threads / p->k->group;  // IVPs per CTA
   long long want = (d->batch + per_cta - 1) / per_cta;
   long long cap = (long long)occ * p->num_sms;
+  if (p->k->family == FAMILY_DENSE_CTA && cap > DENSE_CTA_MAX_CTAS) cap = DENSE_CTA_MAX_CTAS;
   p->grid = (int)(want < cap ? want : cap);
   if (p->grid < 1) p->grid = 1;
   return PN_B200_SUCCESS;
@@ -433,7 +453,7 @@ int pn_b200_solve_save_at(const pn_b200_desc* desc, const double* u0, const doub
   a.sigma0 = output_scale0;
   a.ticket = (unsigned long long*)workspace;
   a.cond = (double*)((char*)workspace + p.ws_ticket);
-  a.wide_d = (p.k->family == FAMILY_WIDE) ? desc->d : 0;
+  a.wide_d = (p.k->family == FAMILY_WIDE || p.k->family == FAMILY_DENSE_CTA) ? desc->d : 0;
   a.wide_smem_means = p.wide_smem_means;
   a.wide_mean = (double*)((char*)workspace + p.ws_ticket + p.ws_cond);
   a.out_scale = output_scale;
@@ -509,6 +529,7 @@ int pn_b200_solve_save_at(const pn_b200_desc* desc, const double* u0, const doub
   s.chol_per_dim = (p.k->family == FAMILY_GROUP_BDIAG) ? 1 : 0;
   s.wide_d = a.wide_d;
   s.wide_mean = a.wide_mean;
+  s.wide_ctas = p.grid;
   s.cond = a.cond;
   s.status = status;
   s.u = u;

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "pn_dense_cta_kernel.cuh"
 #include "pn_dense_kernel.cuh"
 #include "pn_dense_rows_kernel.cuh"
 #include "pn_lml_kernel.cuh"
@@ -17,7 +18,8 @@ enum : int {
   FAMILY_GROUP_BDIAG = 2, // lane per dimension, per-dimension factors (blockdiag)
   FAMILY_DENSE = 3,       // warp per IVP, D x D factors in shared memory (dense, d > 1)
   FAMILY_WIDE = 4,        // CTA per IVP, isotropic, runtime dimension (Brusselator d = 2N up to 4096)
-  FAMILY_DENSE_ROWS = 5   // 16 or 32 lanes per IVP, register-resident Householder columns (dense, D <= 32)
+  FAMILY_DENSE_ROWS = 5,  // 16 or 32 lanes per IVP, register-resident Householder columns (dense, D <= 32)
+  FAMILY_DENSE_CTA = 6    // CTA per IVP, dense with a large runtime dimension, blocked QR on the FP64 tensor path
 };
 inline bool family_is_dense(int family) { return family == FAMILY_DENSE || family == FAMILY_DENSE_ROWS; }
 
@@ -209,6 +211,53 @@ struct WideInstance {
   }
 };
 
+// dense factorisation with a large runtime dimension: CTA per IVP, blocked Householder QR + DMMA products
+template <class Prob, int NU, int STRAT, int NB>
+struct DenseCtaInstance {
+  static cudaError_t launch_solve(const SolveArgs& a, int grid, size_t smem, cudaStream_t s) {
+    cta::pn_dense_cta_kernel<Prob, NU, STRAT, NB><<<grid, cta::T, smem, s>>>(a);
+    return cudaGetLastError();
+  }
+  static cudaError_t launch_smooth(const SmoothArgs& a, cudaStream_t s) {
+    cta::CtaSmoothArgs w;
+    w.B = a.B; w.K = a.K; w.d = a.wide_d; w.n = NU + 1; w.cond = a.cond; w.scratch = a.wide_mean; w.status = a.status;
+    w.u = a.u; w.u_std = a.u_std; w.marg_mean = a.marg_mean; w.marg_chol = a.marg_chol;
+    const size_t smem = cta::smem_doubles<NB>((NU + 1) * a.wide_d) * sizeof(double);
+    auto kern = cta::pn_dense_cta_smooth_kernel<STRAT, NB>;
+    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ce != cudaSuccess) return ce;
+    const int grid = (int)(a.B < a.wide_ctas ? a.B : a.wide_ctas);
+    kern<<<grid, cta::T, smem, s>>>(w);
+    return cudaGetLastError();
+  }
+  static KernelEntry entry() {
+    KernelEntry e;
+    e.launch_sample = nullptr;
+    e.launch_lml = nullptr;
+    e.ctx_doubles = 0;
+    e.solve_func_sliced = nullptr;
+    e.launch_solve_sliced = nullptr;
+    e.family = FAMILY_DENSE_CTA;
+    e.group = cta::T;
+    e.dv = 1;
+    e.problem = Prob::ID;
+    e.nu = NU;
+    e.strategy = STRAT;
+    e.N = NU + 1;
+    e.D = 0;  // runtime dimension
+    e.Q = Prob::Q;
+    e.P = Prob::P;
+    e.slot_doubles = 0;  // runtime: cta::slot_doubles
+    e.smem_doubles = NB; // runtime: cta::smem_doubles<NB>; this field carries the panel width
+    e.threads = cta::T;
+    e.has_jac = Prob::HAS_JAC;
+    e.solve_func = (const void*)&cta::pn_dense_cta_kernel<Prob, NU, STRAT, NB>;
+    e.launch_solve = &launch_solve;
+    e.launch_smooth = &launch_smooth;
+    return e;
+  }
+};
+
 struct Registrar {
   explicit Registrar(const KernelEntry& e) { register_kernel(e); }
 };
@@ -224,6 +273,8 @@ struct Registrar {
   static ::pn::Registrar PN_CAT(pn_reg_, __COUNTER__)(::pn::DenseInstance<::pn::Prob, NU, STRAT, WARPS>::entry())
 #define PN_REGISTER_DENSE_ROWS(Prob, NU, STRAT, LANES, WARPS) \
   static ::pn::Registrar PN_CAT(pn_reg_, __COUNTER__)(::pn::DenseRowsInstance<::pn::Prob, NU, STRAT, LANES, WARPS>::entry())
+#define PN_REGISTER_DENSE_CTA(Prob, NU, STRAT, NB) \
+  static ::pn::Registrar PN_CAT(pn_reg_, __COUNTER__)(::pn::DenseCtaInstance<::pn::cta::Prob, NU, STRAT, NB>::entry())
 #define PN_REGISTER_WIDE(Prob, NU, STRAT) \
   static ::pn::Registrar PN_CAT(pn_reg_, __COUNTER__)(::pn::WideInstance<::pn::Prob, NU, STRAT, 128>::entry())
 #define PN_REGISTER_SCALAR_T(Prob, NU, STRAT, THREADS) \

@@ -17,7 +17,8 @@ struct SmoothArgs {
   int dv;              // lanes ("virtual members") per IVP: 1, or d for the lane-per-dimension kernels
   int chol_per_dim;    // marg_chol layout: 1 -> [B][K][d][N][N] (blockdiag), 0 -> [B][K][N][N]
   int wide_d;          // wide (CTA-per-IVP) kernels: runtime ODE dimension, else 0
-  double* wide_mean;   // wide kernels: per-member mean scratch [B][3][n][d]
+  double* wide_mean;   // wide kernels: per-member mean scratch [B][3][n][d]; dense CTA kernels: per-CTA scratch
+  long long wide_ctas; // dense CTA kernels: CTAs the scratch has room for
   const double* cond;  // [B*dv][K][SLOT]
   const int32_t* status;
   double* u;           // [B][K][D]

@@ -80,6 +80,13 @@ typedef struct {
    * the lane-per-dimension (G <= 32) and CTA-per-IVP (G = 128) CUDA kernels use.  Any order is a
    * faithful restatement; this knob only exists so that comparisons can be bit-exact. */
   int32_t reduction_group;
+  /* Dense factorisation with d > 1 only.  0: the unblocked column-by-column Householder QR / back
+   * substitution of pn_linalg.c (what the warp-per-IVP CUDA kernels reproduce, D <= 40).  nb > 0:
+   * panel-blocked compact-WY QR with panels of nb columns and blocked back substitution in the
+   * operation order of the CTA-per-IVP tensor-core kernel (pn_blocked.c).  Both are Householder QRs
+   * of the same matrices: results agree to rounding (tests/test_oracle_blocked.py), and the blocked
+   * order exists so that the large-D GPU kernel can be compared bit for bit. */
+  int32_t dense_block;
 } pn_oracle_config;
 
 /* ---- deterministic elementary functions (shared contract with the kernel) ---- */

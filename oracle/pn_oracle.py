@@ -50,6 +50,7 @@ class Config(C.Structure):
         ("max_attempts", C.c_int64),
         ("num_params", C.c_int32),
         ("reduction_group", C.c_int32),
+        ("dense_block", C.c_int32),
     ]
 
 
@@ -64,7 +65,7 @@ class AttemptInfo(C.Structure):
 
 def build(force=False):
     """Compile oracle/libpn_oracle.so with gcc (see oracle/Makefile)."""
-    srcs = ["pn_linalg.c", "pn_problems.c", "pn_solver.c", "pn_oracle.h", "pn_internal.h", "Makefile"]
+    srcs = ["pn_linalg.c", "pn_blocked.c", "pn_problems.c", "pn_solver.c", "pn_oracle.h", "pn_internal.h", "Makefile"]
     if not force and os.path.exists(_LIB_PATH):
         newest = max(os.path.getmtime(os.path.join(_HERE, s)) for s in srcs)
         if os.path.getmtime(_LIB_PATH) >= newest:
@@ -114,6 +115,7 @@ def make_config(
     power_integral=0.3,
     power_proportional=0.4,
     reduction_group=0,
+    dense_block=0,
 ):
     return Config(
         PROBLEMS[problem] if isinstance(problem, str) else int(problem),
@@ -135,6 +137,7 @@ def make_config(
         int(max_attempts),
         int(num_params),
         int(reduction_group),
+        int(dense_block),
     )
 
 
@@ -348,3 +351,36 @@ def solve_fixed_grid(cfg, u0, params, grid, output_scale0=1.0):
     if rc:
         raise ValueError(f"oracle rejected the configuration (rc={rc})")
     return {"u": u, "u_std": u_std, "error_norms": en}
+
+
+QR_SHAPES = {"full": 0, "toptri_botfull": 1, "topfull_bottri": 2}
+
+
+def qr_blocked(M, ncols=None, shape="full", ntop=0, nb=16):
+    """Blocked Householder QR (R only) of a copy of M in the CUDA kernel's operation order (pn_blocked.c)."""
+    M = np.array(M, dtype=np.float64, order="C")
+    rows, cols = M.shape
+    lib().pn_qr_blocked(_dptr(M), C.c_int(cols), C.c_int(rows), C.c_int(cols), C.c_int(cols if ncols is None else ncols),
+                        C.c_int(QR_SHAPES[shape]), C.c_int(ntop), C.c_int(nb))  # fmt: skip
+    return M
+
+
+def solve_upper_blocked(R, B, nb=64):
+    """X = R^{-1} B by blocked back substitution in the CUDA kernel's operation order (pn_blocked.c)."""
+    R, B = _f64(R), _f64(B)
+    n, c = B.shape
+    X = np.zeros((n, c))
+    lib().pn_solve_upper_blocked(_dptr(R), C.c_int(R.shape[1]), _dptr(B), C.c_int(c), _dptr(X), C.c_int(c), C.c_int(n),
+                                 C.c_int(c), C.c_int(nb))  # fmt: skip
+    return X
+
+
+def gemm_chain(A, B, C0=None, neg=False):
+    """C = (C0 or 0) -/+ A B with the ascending-k fma chain per element (the tensor-core product contract)."""
+    A, B = _f64(A), _f64(B)
+    M, K = A.shape
+    N = B.shape[1]
+    C0 = _f64(C0) if C0 is not None else None
+    out = np.zeros((M, N))
+    lib().pn_gemm_chain(_dptr(out), _dptr(A), _dptr(B), C.c_int(M), C.c_int(N), C.c_int(K), _dptr(C0), C.c_int(1 if neg else 0))
+    return out

@@ -75,6 +75,7 @@ typedef struct {
   int n, d, q, nu;
   int F, N, C, Ctot, r;
   int dense;         /* r > 1 path */
+  int blk;           /* > 0: blocked QR / back substitution with panels of blk columns (dense only) */
   double *A, *LQ;    /* N x N (Kronecker-expanded for dense d>1) */
   double fact[PN_MAX_N], invfact[PN_MAX_N];
   double inv_sqrt_d, inv_sqrt_C;
@@ -125,6 +126,8 @@ static int engine_init(engine *E, const pn_oracle_config *cfg) {
   }
   if (cfg->correction == PN_CORR_TS1 && !pn_problem_has_jacobian(cfg->problem)) return -4;
   E->dense = (E->r > 1);
+  E->blk = (E->dense && cfg->dense_block > 0) ? cfg->dense_block : 0;
+  if (E->blk > 64) return -5;
   int N = E->N;
   double a1[PN_MAX_N * PN_MAX_N], lq[PN_MAX_N * PN_MAX_N];
   pn_oracle_prior(cfg->nu, a1, lq);
@@ -257,6 +260,17 @@ static double sum_squares(const engine *E, const double *v, int k) {
   return r;
 }
 
+/* QR (R only) of a rows x cols matrix with leading dimension cols; only the first ncols columns are
+ * triangularised.  `shape` / `ntop` name the structural zeros of the stacked matrix: the unblocked
+ * routine ignores them (zeros are exact no-ops in its full loops), the blocked one uses them to pick
+ * the active rows of a panel. */
+static void eng_qr(const engine *E, double *M, int rows, int cols, int ncols, int shape, int ntop) {
+  if (E->blk > 0)
+    pn_qr_blocked(M, cols, rows, cols, ncols, shape, ntop, E->blk);
+  else
+    pn_qr_r_partial(M, rows, cols, ncols);
+}
+
 /* predicted mean: m_p = pinv*m, m_ext_p = A m_p, m_ext = p*m_ext_p */
 static void predict_mean(engine *E, const double *mean) {
   int N = E->N, Ct = E->Ctot;
@@ -288,7 +302,7 @@ static void merge_one(engine *E, const double *G1, const double *g1, const doubl
       M[i * N + j] = T[j * N + i];
       M[(N + i) * N + j] = L1[j * N + i];
     }
-  pn_qr_r(M, 2 * N, N);
+  eng_qr(E, M, 2 * N, N, N, PN_QR_TOPFULL_BOTTRI, N);
   for (int i = 0; i < N; ++i)
     for (int j = 0; j < N; ++j) Lo[i * N + j] = (j <= i) ? M[j * N + i] : 0.0;
   memcpy(Go, Gtmp, sizeof(double) * N * N);
@@ -315,7 +329,7 @@ static void marginalise_one(engine *E, const double *m, const double *L, const d
       M[i * N + j] = T[j * N + i];
       M[(N + i) * N + j] = Lam[j * N + i];
     }
-  pn_qr_r(M, 2 * N, N);
+  eng_qr(E, M, 2 * N, N, N, PN_QR_TOPFULL_BOTTRI, N);
   for (int i = 0; i < N; ++i)
     for (int j = 0; j < N; ++j) Lo[i * N + j] = (j <= i) ? M[j * N + i] : 0.0;
   for (int i = 0; i < N; ++i)
@@ -342,7 +356,7 @@ static void predict_cov_one(engine *E, const double *L, double sigma, double *L_
         M[i * N + j] = sigma * E->LQ[j * N + i];
         M[(N + i) * N + j] = AL[j * N + i];
       }
-    pn_qr_r(M, 2 * N, N);
+    eng_qr(E, M, 2 * N, N, N, PN_QR_TOPTRI_BOTFULL, N);
     for (int i = 0; i < N; ++i)
       for (int j = 0; j < N; ++j) L_ext[i * N + j] = (j <= i) ? E->p[i] * M[j * N + i] : 0.0;
     return;
@@ -359,14 +373,17 @@ static void predict_cov_one(engine *E, const double *L, double sigma, double *L_
   /* only the first N columns are triangularised: R_Y, R_12 are final after that, and the
    * lower-right block B (N x N, full) satisfies B^T B = R_XY^T R_XY, i.e. B^T is a valid
    * (non-triangular) square-root factor of the backward noise; the merge below re-triangularises */
-  pn_qr_r_partial(M, W2, W2, N);
+  eng_qr(E, M, W2, W2, N, PN_QR_TOPTRI_BOTFULL, N);
   double *RY = E->Mq, *R12 = E->Gp, *X = E->X;
   for (int i = 0; i < N; ++i)
     for (int j = 0; j < N; ++j) {
       RY[i * N + j] = M[i * W2 + j];
       R12[i * N + j] = M[i * W2 + N + j];
     }
-  pn_solve_upper(RY, R12, X, N, N); /* X = RY^{-1} R12 ; G_p = X^T */
+  if (E->blk > 0)
+    pn_solve_upper_blocked(RY, N, R12, N, X, N, N, N, PN_TRSM_BLOCK);
+  else
+    pn_solve_upper(RY, R12, X, N, N); /* X = RY^{-1} R12 ; G_p = X^T */
   /* g_p = m_p - G_p m_ext_p ; un-precondition */
   double *Gn = E->AL; /* AL no longer needed */
   double *Ln = E->Lamp;
@@ -453,7 +470,8 @@ static void calibrate_and_estimate(engine *E, double dt) {
         for (int i = 0; i < N; ++i) acc = fma(E->h[l * N + i] * E->p[i], E->LQ[i * N + j], acc);
         Rs[j * d + l] = acc;
       }
-    pn_qr_r(Rs, N, d);
+    /* rows beyond block q are exactly zero (LQ is lower triangular, H has no entries beyond block q) */
+    eng_qr(E, Rs, (E->q + 1) * d, d, d, PN_QR_FULL, 0);
     /* y = R^{-T} z */
     double *y = E->fbuf;
     pn_solve_upper_transposed(Rs, E->z, y, d, 1);
@@ -496,7 +514,7 @@ static void correct_cov_one(engine *E, const double *L_ext, double *L_new) {
     double *Rm = E->Rm; /* N x r */
     for (int j = 0; j < N; ++j)
       for (int l = 0; l < r; ++l) Rm[j * r + l] = HL[l * N + j];
-    pn_qr_r(Rm, N, r); /* R_marg in the top r x r */
+    eng_qr(E, Rm, N, r, r, PN_QR_FULL, 0); /* R_marg in the top r x r */
     /* W = L_ext HL^T (N x r);  gain^T = (R^T R)^{-1} W^T */
     double *Wt = E->W; /* r x N : W^T */
     for (int l = 0; l < r; ++l)
@@ -516,7 +534,7 @@ static void correct_cov_one(engine *E, const double *L_ext, double *L_new) {
         M[j * N + i] = acc;
       }
   }
-  pn_qr_r(M, N, N);
+  eng_qr(E, M, N, N, N, PN_QR_FULL, 0);
   for (int i = 0; i < N; ++i)
     for (int j = 0; j < N; ++j) L_new[i * N + j] = (j <= i) ? M[j * N + i] : 0.0;
 }
