@@ -176,6 +176,7 @@ __global__ void pn_order_scatter_kernel(const double* tol, long long B, unsigned
   if (i < B) order[atomicAdd(&cursor[order_bucket(tol[2 * i], tol[2 * i + 1])], 1u)] = i;
 }
 
+constexpr long long COOP_MAX_BATCH = 0;        // largest ensemble the cooperative scalar kernel is chosen for (0: opt-in only)
 constexpr long long DENSE_CTA_MAX_CTAS = 148;  // per-CTA scratch regions the workspace provides (SMs of a B200)
 static size_t dense_cta_smem_bytes(const KernelEntry* k, const pn_b200_desc* d) {
   const int Dn = (d->nu + 1) * d->d;
@@ -200,6 +201,20 @@ static int resolve(const pn_b200_desc* d, const KernelEntry** out) {
                    (d->factorisation == PN_B200_DENSE && d->d == 1) ||
                    (d->factorisation == PN_B200_BLOCKDIAG && d->d == 1 && d->correction == PN_B200_TS0);
   if (scalar_ok) k = find_kernel(FAMILY_SCALAR, d->problem, d->nu, d->strategy, d->d);
+  // Scalar ODEs, n lanes per IVP instead of one (pn_coop_kernel.cuh): opt-in.  Measured on B200 (profiles/
+  // r02_small_ensembles.txt): one attempted step is a ~5k-cycle chain of dependent fp64 operations (12 serial
+  // reflectors + the controller's log / exp), which neither mapping can shorten; spreading the columns over
+  // n lanes removes arithmetic from the lanes but adds exchanges to the chain, and ends up 15-60 % SLOWER than
+  // the thread-per-IVP kernel at every ensemble size (1 member: 81 vs 70 ms; 8,192: 126 vs 78 ms).  It stays
+  // in the tree as a bit-identical cross-check and for experiments: PN_B200_COOP_MAX_BATCH=<members>.
+  if (k && d->d == 1 && !getenv("PN_B200_NO_COOP")) {
+    long long coop_max = COOP_MAX_BATCH;
+    if (const char* e = getenv("PN_B200_COOP_MAX_BATCH")) coop_max = atoll(e);
+    if (d->batch <= coop_max) {
+      const KernelEntry* kc = find_kernel(FAMILY_COOP, d->problem, d->nu, d->strategy, d->d);
+      if (kc) k = kc;
+    }
+  }
   // lane-per-dimension family: blockdiag EKF0, and isotropic EKF0 for problems too wide for one thread
   if (!k && d->correction == PN_B200_TS0 && d->factorisation == PN_B200_BLOCKDIAG)
     k = find_kernel(FAMILY_GROUP_BDIAG, d->problem, d->nu, d->strategy, d->d);
@@ -222,7 +237,7 @@ static int resolve(const pn_b200_desc* d, const KernelEntry** out) {
   if (!k && d->correction == PN_B200_TS0 && d->factorisation == PN_B200_ISOTROPIC && d->d >= 4 && d->d <= 4096 &&
       (d->d % 2) == 0)
     k = find_kernel(FAMILY_WIDE, d->problem, d->nu, d->strategy, 0);
-  if (k && k->group > 1 && (d->flags & PN_B200_FLAG_RECORD))
+  if (k && k->group > 1 && k->family != FAMILY_COOP && (d->flags & PN_B200_FLAG_RECORD))
     return fail(PN_B200_ERR_UNSUPPORTED, "trajectory recording is implemented for the thread-per-IVP kernels");
   if (!k) {
     char buf[256];
@@ -244,6 +259,7 @@ static int make_plan(const pn_b200_desc* d, Plan* p, bool need_device) {
                 ? (size_t)p->k->smem_doubles * (p->k->threads / 32) * sizeof(double)  // per warp
                 : (size_t)p->k->smem_doubles * p->k->threads * sizeof(double);        // per thread
   if (p->k->family == FAMILY_DENSE_CTA) p->smem = dense_cta_smem_bytes(p->k, d);
+  if (p->k->family == FAMILY_COOP) p->smem = (size_t)p->k->smem_doubles * sizeof(double);  // per CTA
   if (p->k->family == FAMILY_WIDE) {
     p->smem += ((size_t)2 * d->d + p->k->threads / 32 + 2) * sizeof(double);
     // few members (at most one per SM: no occupancy to lose) whose mean arrays fit next to the rest
@@ -310,7 +326,8 @@ static int make_plan(const pn_b200_desc* d, Plan* p, bool need_device) {
     g_geom.push_back({dev, p->k, p->smem, p->num_sms, occ});
   }
   const int occ = p->ctas_per_sm;
-  const long long per_cta = (p->k->family == FAMILY_WIDE) ? 1 : p->k->threads / p->k->group;  // IVPs per CTA
+  long long per_cta = (p->k->family == FAMILY_WIDE) ? 1 : p->k->threads / p->k->group;  // IVPs per CTA
+  if (p->k->family == FAMILY_COOP) per_cta = (long long)(p->k->threads / 32) * (32 / p->k->group);
   long long want = (d->batch + per_cta - 1) / per_cta;
   long long cap = (long long)occ * p->num_sms;
   if (p->k->family == FAMILY_DENSE_CTA && cap > DENSE_CTA_MAX_CTAS) cap = DENSE_CTA_MAX_CTAS;

@@ -46,7 +46,9 @@ PN_DEV void dmma(double& c0, double& c1, double a, double b) {
 
 // CTA-order sum (oracle: cta_reduce): butterfly over the 32 lanes, then the warps in ascending order.
 // red: [WARPS] doubles of shared memory.  Every thread gets the total.  Two barriers.
-PN_DEV double cta_sum(double v, double* red) {
+PN_DEV double cta_sum(double v, int red_off) {
+  extern __shared__ double cta_sh[];
+  double* red = cta_sh + red_off;
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, off);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
@@ -59,7 +61,7 @@ PN_DEV double cta_sum(double v, double* red) {
 }
 
 // sum of squares of v[0..k) in the oracle's reduction_group = 256 order
-PN_DEV double cta_sum_squares(const double* v, int k, double* red) {
+PN_DEV double cta_sum_squares(const double* v, int k, int red) {
   double acc = 0.0;
   for (int c = threadIdx.x; c < k; c += T) acc = fma(v[c], v[c], acc);
   return cta_sum(acc, red);
@@ -72,9 +74,10 @@ PN_DEV double cta_sum_squares(const double* v, int k, double* red) {
 // ------------------------------------------------------------------------------------------------
 template <bool NEG>
 __device__ __noinline__ void gemm(double* C, int ldc, const double* A, int lda, bool a_kmajor, const double* B, int ldb,
-                                  int M, int N, int K, const double* C0, int ldc0, double* smem) {
-  double* Bs = smem;             // [16][68]
-  double* As = smem + 16 * 68;   // m-major: [64][20]; k-major: [16][68]
+                                  int M, int N, int K, const double* C0, int ldc0) {
+  extern __shared__ double cta_sh[];
+  double* Bs = cta_sh;             // [16][68]
+  double* As = cta_sh + 16 * 68;   // m-major: [64][20]; k-major: [16][68]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int wm = (warp >> 2) * 32, wn = (warp & 3) * 16;  // warp tile 32 x 16 inside the 64 x 64 CTA tile
   for (int i0 = 0; i0 < M; i0 += 64) {
@@ -158,26 +161,76 @@ __device__ __noinline__ void gemm(double* C, int ldc, const double* A, int lda, 
 // the reflectors.  On exit the upper triangle holds R; entries below the diagonal are NOT cleared
 // (nobody reads them).
 // ------------------------------------------------------------------------------------------------
+// Shared-memory layout of the QR (offsets in doubles from the start of the dynamic shared memory; the
+// functions below address it through the extern array so that the compiler emits LDS / STS, not generic
+// loads).  The panel sits at offset 0 and is aliased by the GEMM tiles (never live at the same time).
 template <int NB>
 struct QrSmem {
   static constexpr int LDP = NB + 4;  // (LDP mod 16) == 4: conflict-free tensor fragment reads
-  double* P;     // [hmax4][LDP] panel / V
-  double* Tm;    // [NB][NB]
-  double* red;   // [WARPS][NB]
-  double* v0;    // [NB]
-  double* beta;  // [NB]
-  double* wy;    // [WARPS][2][NB][8]
-  __host__ __device__ static constexpr int fixed_doubles() { return NB * NB + WARPS * NB + 2 * NB + WARPS * 2 * NB * 8; }
-  __host__ __device__ static int panel_doubles(int hmax) { return ((hmax + 3) / 4 * 4) * LDP; }
+  int P;     // [hmax4][LDP] panel / V
+  int Tm;    // [NB][NB]
+  int red;   // [WARPS][NB]
+  int v0;    // [NB]
+  int beta;  // [NB]
+  int wf;    // [WARPS][NB]   per warp: f (columns right of the pivot) / Gram entries S (columns left of it)
+  int wy;    // [WARPS][2][NB][16]
+  __host__ __device__ static constexpr int fixed_doubles() { return NB * NB + 2 * WARPS * NB + 2 * NB + WARPS * 2 * NB * 16; }
+  __host__ __device__ static int panel_doubles(int hmax) { return ((hmax + 7) / 8 * 8) * LDP; }
+  __host__ __device__ void layout(int hmax) {
+    const int panel = panel_doubles(hmax);
+    int o = panel > GEMM_SMEM ? panel : GEMM_SMEM;
+    P = 0;
+    Tm = o;   o += NB * NB;
+    red = o;  o += WARPS * NB;
+    v0 = o;   o += NB;
+    beta = o; o += NB;
+    wf = o;   o += WARPS * NB;
+    wy = o;
+  }
 };
+
+// Warp sum of NB per-lane partial values by a TRANSPOSED butterfly: level by level a lane keeps half of its
+// values and sends the other half to its xor partner, so the tree of additions per value is exactly the
+// plain butterfly's (xor 16, 8, 4, 2, 1; a + b is commutative) at NB - 1 instead of 5 NB exchanges.
+// On return the lane holds the warp total of value `cidx`.
+template <int NB>
+PN_DEV double warp_sum_transposed(const double (&part)[NB], int lane, int& cidx) {
+  double q[NB];
+#pragma unroll
+  for (int i = 0; i < NB; ++i) q[i] = part[i];
+  cidx = 0;
+#pragma unroll
+  for (int lvl = 0; lvl < 5; ++lvl) {
+    const int off = 16 >> lvl;
+    const int n = (NB >> lvl) > 0 ? (NB >> lvl) : 1;
+    if (n > 1) {
+      const int half = n / 2;
+      const bool hi = (lane & off) != 0;
+#pragma unroll
+      for (int i = 0; i < half; ++i) {
+        const double send = hi ? q[i] : q[i + half];
+        const double keep = hi ? q[i + half] : q[i];
+        q[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+      cidx = (cidx << 1) | (hi ? 1 : 0);
+    } else {
+      q[0] = q[0] + __shfl_xor_sync(0xffffffffu, q[0], off);
+    }
+  }
+  return q[0];
+}
 
 template <int NB>
 __device__ __noinline__ void qr_blocked(double* M, int ld, int rows, int cols, int ncols, int shape, int ntop, const QrSmem<NB>& s) {
   constexpr int LDP = QrSmem<NB>::LDP;
+  extern __shared__ double cta_sh[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   int kmax = rows < cols ? rows : cols;
   if (ncols < kmax) kmax = ncols;
-  double* P = s.P;
+  double* P = cta_sh + s.P;
+  double* Tm = cta_sh + s.Tm;
+  double* red = cta_sh + s.red;
+  double* wf = cta_sh + s.wf + warp * NB;
   for (int j0 = 0; j0 < kmax; j0 += NB) {
     const int w = (kmax - j0 < NB) ? (kmax - j0) : NB;
     // gathered row r of the panel  ->  row of M
@@ -198,13 +251,13 @@ __device__ __noinline__ void qr_blocked(double* M, int ld, int rows, int cols, i
       base2 = j0;
     }
     auto grow = [&](int r) -> int { return (r < split) ? (j0 + r) : (base2 + r); };
-    const int h4 = (h + 3) / 4 * 4;
+    const int h8 = (h + 7) / 8 * 8;
     __syncthreads();
-    for (int e = tid; e < h4 * NB; e += T) {
+    for (int e = tid; e < h8 * NB; e += T) {
       const int r = e / NB, c = e - r * NB;
       P[r * LDP + c] = (r < h && c < w) ? M[(size_t)grow(r) * ld + j0 + c] : 0.0;
     }
-    for (int e = tid; e < NB * NB; e += T) s.Tm[e] = 0.0;
+    for (int e = tid; e < NB * NB; e += T) Tm[e] = 0.0;
     __syncthreads();
     // ---- panel factorisation: one pass + one CTA reduction per column ------------------------------
     for (int jj = 0; jj < w; ++jj) {
@@ -218,38 +271,25 @@ __device__ __noinline__ void qr_blocked(double* M, int ld, int rows, int cols, i
           for (int c = 0; c < NB; ++c) part[c] = fma(x, P[r * LDP + c], part[c]);
         }
       }
-#pragma unroll
-      for (int c = 0; c < NB; ++c) {
-        double v = part[c];
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, off);
-        part[c] = v;
-      }
-      if (lane == 0) {
-#pragma unroll
-        for (int c = 0; c < NB; ++c) s.red[warp * NB + c] = part[c];
-      }
+      int cidx;
+      const double wtot = warp_sum_transposed<NB>(part, lane, cidx);
+      red[warp * NB + cidx] = wtot;
       __syncthreads();
-      double prow[NB];
+      // lane c < NB of every warp: CTA total of column c (warps in ascending order), pivot-row entry
+      const int cl = lane & (NB - 1);
+      double tot = red[cl];
 #pragma unroll
-      for (int c = 0; c < NB; ++c) {
-        double r = s.red[c];
-#pragma unroll
-        for (int ww = 1; ww < WARPS; ++ww) r = r + s.red[ww * NB + c];
-        part[c] = r;                      // tot[c]
-        prow[c] = P[jj * LDP + c];        // pivot row before the update
-      }
-      double sigma2 = part[0], alpha = prow[0];
-#pragma unroll
-      for (int c = 1; c < NB; ++c) {
-        sigma2 = (c == jj) ? part[c] : sigma2;
-        alpha = (c == jj) ? prow[c] : alpha;
-      }
+      for (int ww = 1; ww < WARPS; ++ww) tot = tot + red[ww * NB + cl];
+      const double prow = P[jj * LDP + cl];
+      const double sigma2 = __shfl_sync(0xffffffffu, tot, jj);
+      const double alpha = __shfl_sync(0xffffffffu, prow, jj);
       const Reflector rf = make_reflector(alpha, sigma2);
-      __syncthreads();  // everybody has read red[] and the pivot row
+      const double fS = fma(rf.v0, prow, tot);  // right of the pivot: v^T column; left of it: Gram entry S
+      if (lane < NB) wf[cl] = (cl > jj) ? fS * rf.g : fS;
+      __syncthreads();  // pivot row and red[] have been read by everybody; wf is complete
       double f[NB];
 #pragma unroll
-      for (int c = 0; c < NB; ++c) f[c] = (c > jj) ? (fma(rf.v0, prow[c], part[c]) * rf.g) : 0.0;
+      for (int c = 0; c < NB; ++c) f[c] = wf[c];
       for (int r = tid; r < h; r += T) {
         if (r > jj) {
           const double x = P[r * LDP + jj];
@@ -261,27 +301,17 @@ __device__ __noinline__ void qr_blocked(double* M, int ld, int rows, int cols, i
       if (tid == (jj % T)) {  // owner of the pivot row
 #pragma unroll
         for (int c = 0; c < NB; ++c)
-          if (c > jj) P[jj * LDP + c] = fma(-f[c], rf.v0, prow[c]);
+          if (c > jj) P[jj * LDP + c] = fma(-f[c], rf.v0, P[jj * LDP + c]);
         P[jj * LDP + jj] = rf.v0;
-        s.v0[jj] = rf.v0;
-        s.beta[jj] = rf.beta;
-        s.Tm[jj * NB + jj] = rf.g;
+        cta_sh[s.v0 + jj] = rf.v0;
+        cta_sh[s.beta + jj] = rf.beta;
+        Tm[jj * NB + jj] = rf.g;
       }
-      if (tid < jj) {  // T[0:jj, jj] = -g T[0:jj, 0:jj] S,  S[k] = v_jj^T v_k (pivot-row term last)
+      if (tid < jj) {  // T[0:jj, jj] = -g T[0:jj, 0:jj] S   (warp 0: its wf holds S[k] for k < jj)
         double acc = 0.0;
-        for (int k = tid; k < jj; ++k) {
-          double sk = 0.0, pk = 0.0;
-#pragma unroll
-          for (int c = 0; c < NB; ++c) {
-            sk = (c == k) ? part[c] : sk;
-            pk = (c == k) ? prow[c] : pk;
-          }
-          acc = fma(s.Tm[tid * NB + k], fma(rf.v0, pk, sk), acc);
-        }
-        s.Tm[tid * NB + jj] = (-rf.g) * acc;
+        for (int k = tid; k < jj; ++k) acc = fma(Tm[tid * NB + k], wf[k], acc);
+        Tm[tid * NB + jj] = (-rf.g) * acc;
       }
-      // next column's pass touches rows > jj + 1 of the panel and writes red[] only after its own pass:
-      // the barrier after that pass orders everything above
     }
     __syncthreads();
     // ---- R entries of the panel back to M; V = panel with the entries above the pivots cleared -----
@@ -289,7 +319,7 @@ __device__ __noinline__ void qr_blocked(double* M, int ld, int rows, int cols, i
       const int r = e / w, c = e - r * w;
       double val = 0.0;
       if (r < c) val = P[r * LDP + c];
-      if (r == c) val = s.beta[c];
+      if (r == c) val = cta_sh[s.beta + c];
       M[(size_t)(j0 + r) * ld + j0 + c] = val;
     }
     __syncthreads();
@@ -298,59 +328,148 @@ __device__ __noinline__ void qr_blocked(double* M, int ld, int rows, int cols, i
       if (r < c) P[r * LDP + c] = 0.0;
     }
     __syncthreads();
-    // ---- trailing columns, one 8-column tile per warp at a time -----------------------------------
+    // ---- trailing columns: 16 columns per warp at a time, as two interleaved 8-column tensor tiles ----
+    // (tile 0 = even columns, tile 1 = odd columns: a lane's two B-fragment entries are adjacent in memory)
     const int c_first = j0 + w;
-    const int ntiles = (cols - c_first + 7) / 8;
-    double* w0s = s.wy + (size_t)warp * 2 * NB * 8;
-    double* ys = w0s + NB * 8;
+    const int ntiles = (cols - c_first + 15) / 16;
+    const bool vec_ok = ((ld & 1) == 0) && ((c_first & 1) == 0) && ((((size_t)M) & 15) == 0);
+    double* w0s = cta_sh + s.wy + (size_t)warp * 2 * NB * 16;
+    double* ys = w0s + NB * 16;
+    const int nchunk = (h + 3) / 4;
+    constexpr int U = 8;
     for (int tile = warp; tile < ntiles; tile += WARPS) {
-      const int c0 = c_first + tile * 8;
-      const bool colg = (c0 + g) < cols;
-      // W0 = V^T C  (NB x 8): chain over the gathered rows, ascending
-      double acc[NB / 8][2];
+      const int c0 = c_first + tile * 16;
+      const int cA = c0 + 2 * g;
+      auto loadB = [&](int chunk, double& b0, double& b1) {
+        const int r = chunk * 4 + t;
+        b0 = 0.0;
+        b1 = 0.0;
+        if (chunk < nchunk && r < h) {
+          const double* rowp = M + (size_t)grow(r) * ld;
+          if (vec_ok && cA + 1 < cols) {
+            const double2 v = *reinterpret_cast<const double2*>(rowp + cA);
+            b0 = v.x;
+            b1 = v.y;
+          } else {
+            if (cA < cols) b0 = rowp[cA];
+            if (cA + 1 < cols) b1 = rowp[cA + 1];
+          }
+        }
+      };
+      // W0 = V^T C  (NB x 16): chain over the gathered rows, ascending
+      double acc[NB / 8][2][2];
 #pragma unroll
-      for (int mt = 0; mt < NB / 8; ++mt) acc[mt][0] = acc[mt][1] = 0.0;
-#pragma unroll 4
-      for (int k0 = 0; k0 < h4; k0 += 4) {
-        const int r = k0 + t;
-        const double b = (r < h && colg) ? M[(size_t)grow(r) * ld + c0 + g] : 0.0;
+      for (int mt = 0; mt < NB / 8; ++mt) acc[mt][0][0] = acc[mt][0][1] = acc[mt][1][0] = acc[mt][1][1] = 0.0;
+      double bc0[U], bc1[U];
 #pragma unroll
-        for (int mt = 0; mt < NB / 8; ++mt) dmma(acc[mt][0], acc[mt][1], P[r * LDP + mt * 8 + g], b);
+      for (int u = 0; u < U; ++u) loadB(u, bc0[u], bc1[u]);
+      for (int blk = 0; blk * U < nchunk; ++blk) {
+        double bn0[U], bn1[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) loadB((blk + 1) * U + u, bn0[u], bn1[u]);  // in flight while this block computes
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int chunk = blk * U + u;
+          if (chunk < nchunk) {
+            const int r = chunk * 4 + t;
+#pragma unroll
+            for (int mt = 0; mt < NB / 8; ++mt) {
+              const double a = P[r * LDP + mt * 8 + g];
+              dmma(acc[mt][0][0], acc[mt][0][1], a, bc0[u]);
+              dmma(acc[mt][1][0], acc[mt][1][1], a, bc1[u]);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          bc0[u] = bn0[u];
+          bc1[u] = bn1[u];
+        }
       }
+      // C fragment (row g, column index 2t + hh of tile tau) -> column offset 2 (2t + hh) + tau of the 16
 #pragma unroll
-      for (int mt = 0; mt < NB / 8; ++mt) {
-        w0s[(mt * 8 + g) * 8 + 2 * t] = acc[mt][0];
-        w0s[(mt * 8 + g) * 8 + 2 * t + 1] = acc[mt][1];
-      }
+      for (int mt = 0; mt < NB / 8; ++mt)
+#pragma unroll
+        for (int tau = 0; tau < 2; ++tau)
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) w0s[(mt * 8 + g) * 16 + 4 * t + 2 * hh + tau] = acc[mt][tau][hh];
       __syncwarp();
       // Y = T^T W0: Y[a][col] = sum_{i <= a} T[i][a] W0[i][col], ascending i
       {
-        const int col = lane & 7;
+        const int col = lane & 15;
 #pragma unroll
-        for (int q = 0; q < NB / 4; ++q) {
-          const int a = (lane >> 3) + 4 * q;
+        for (int q = 0; q < NB / 2; ++q) {
+          const int a = (lane >> 4) + 2 * q;
           double y = 0.0;
-          for (int i = 0; i <= a; ++i) y = fma(s.Tm[i * NB + a], w0s[i * 8 + col], y);
-          ys[a * 8 + col] = y;
+          for (int i = 0; i <= a; ++i) y = fma(Tm[i * NB + a], w0s[i * 16 + col], y);
+          ys[a * 16 + col] = y;
         }
       }
       __syncwarp();
-      double yb[NB / 4];
+      double yb[2][NB / 4];
 #pragma unroll
-      for (int kk = 0; kk < NB / 4; ++kk) yb[kk] = ys[(4 * kk + t) * 8 + g];
-      // C <- C - V Y: chain over the panel columns, ascending, starting from C
-      const int cc0 = c0 + 2 * t, cc1 = cc0 + 1;
-#pragma unroll 2
-      for (int m0 = 0; m0 < h4; m0 += 8) {
-        const int r = m0 + g;
-        const bool rv = r < h;
-        double* rowp = M + (size_t)(rv ? grow(r) : 0) * ld;
-        double x0 = (rv && cc0 < cols) ? rowp[cc0] : 0.0;
-        double x1 = (rv && cc1 < cols) ? rowp[cc1] : 0.0;
+      for (int kk = 0; kk < NB / 4; ++kk) {
+        yb[0][kk] = ys[(4 * kk + t) * 16 + 2 * g];
+        yb[1][kk] = ys[(4 * kk + t) * 16 + 2 * g + 1];
+      }
+      // C <- C - V Y: chain over the panel columns, ascending, starting from C.  A lane owns 4 adjacent
+      // columns c0 + 4t .. c0 + 4t + 3 of row g of every 8-row tile.
+      const int cX = c0 + 4 * t;
+      const bool vec4 = vec_ok && (cX + 3 < cols);
+      const int nm = (h + 7) / 8;
+      constexpr int UM = 4;
+      auto loadX = [&](int mtile, double (&x)[4]) {
+        const int r = mtile * 8 + g;
+        x[0] = x[1] = x[2] = x[3] = 0.0;
+        if (mtile < nm && r < h) {
+          const double* rowp = M + (size_t)grow(r) * ld;
+          if (vec4) {
+            const double2 v0 = *reinterpret_cast<const double2*>(rowp + cX);
+            const double2 v1 = *reinterpret_cast<const double2*>(rowp + cX + 2);
+            x[0] = v0.x; x[1] = v0.y; x[2] = v1.x; x[3] = v1.y;
+          } else {
 #pragma unroll
-        for (int kk = 0; kk < NB / 4; ++kk) dmma(x0, x1, rv ? -P[r * LDP + 4 * kk + t] : 0.0, yb[kk]);
-        if (rv && cc0 < cols) rowp[cc0] = x0;
-        if (rv && cc1 < cols) rowp[cc1] = x1;
+            for (int e = 0; e < 4; ++e)
+              if (cX + e < cols) x[e] = rowp[cX + e];
+          }
+        }
+      };
+      double xc[UM][4];
+#pragma unroll
+      for (int u = 0; u < UM; ++u) loadX(u, xc[u]);
+      for (int mb = 0; mb < nm; mb += UM) {
+        double xn[UM][4];
+#pragma unroll
+        for (int u = 0; u < UM; ++u) loadX(mb + UM + u, xn[u]);
+#pragma unroll
+        for (int u = 0; u < UM; ++u) {
+          const int mtile = mb + u;
+          const int r = mtile * 8 + g;
+          if (mtile < nm) {
+            const bool rv = r < h;
+#pragma unroll
+            for (int kk = 0; kk < NB / 4; ++kk) {
+              const double a = rv ? -P[r * LDP + 4 * kk + t] : 0.0;
+              dmma(xc[u][0], xc[u][2], a, yb[0][kk]);
+              dmma(xc[u][1], xc[u][3], a, yb[1][kk]);
+            }
+            if (rv) {
+              double* rowp = M + (size_t)grow(r) * ld;
+              if (vec4) {
+                *reinterpret_cast<double2*>(rowp + cX) = make_double2(xc[u][0], xc[u][1]);
+                *reinterpret_cast<double2*>(rowp + cX + 2) = make_double2(xc[u][2], xc[u][3]);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (cX + e < cols) rowp[cX + e] = xc[u][e];
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < UM; ++u)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) xc[u][e] = xn[u][e];
       }
       __syncwarp();
     }
@@ -361,13 +480,13 @@ __device__ __noinline__ void qr_blocked(double* M, int ld, int rows, int cols, i
 // R X = B (R n x n upper, ld ldr; B n x c; X n x c), blocked back substitution
 // (oracle/pn_blocked.c: pn_solve_upper_blocked with nb = TRSM_BLOCK).
 static __device__ __noinline__ void solve_upper_blocked(const double* R, int ldr, const double* B, int ldb, double* X, int ldx,
-                                                 int n, int c, double* smem) {
+                                                 int n, int c) {
   const int nblk = (n + TRSM_BLOCK - 1) / TRSM_BLOCK;
   for (int bi = nblk - 1; bi >= 0; --bi) {
     const int i0 = bi * TRSM_BLOCK, i1 = (i0 + TRSM_BLOCK < n) ? i0 + TRSM_BLOCK : n;
     if (i1 < n) {
       gemm<true>(X + (size_t)i0 * ldx, ldx, R + (size_t)i0 * ldr + i1, ldr, false, X + (size_t)i1 * ldx, ldx, i1 - i0, c,
-                 n - i1, B + (size_t)i0 * ldb, ldb, smem);
+                 n - i1, B + (size_t)i0 * ldb, ldb);
     } else {
       for (int e = threadIdx.x; e < (i1 - i0) * c; e += T) {
         const int i = i0 + e / c, j = e % c;
@@ -535,17 +654,8 @@ __global__ void __launch_bounds__(T, 1) pn_dense_cta_kernel(const __grid_constan
 
   extern __shared__ double smem[];
   QrSmem<NB> qs;
-  {
-    const int panel = QrSmem<NB>::panel_doubles(Dn + NB);
-    double* sp = smem + (panel > GEMM_SMEM ? panel : GEMM_SMEM);
-    qs.P = smem;
-    qs.Tm = sp;       sp += NB * NB;
-    qs.red = sp;      sp += WARPS * NB;
-    qs.v0 = sp;       sp += NB;
-    qs.beta = sp;     sp += NB;
-    qs.wy = sp;       sp += WARPS * 2 * NB * 8;
-  }
-  double* red = qs.red;  // [WARPS] for scalar CTA sums (never live at the same time as a QR)
+  qs.layout(Dn + NB);
+  const int red = qs.red;  // [WARPS] for scalar CTA sums (never live at the same time as a QR)
   __shared__ unsigned long long s_ticket;
   __shared__ double s_bcast[4];
 
@@ -742,7 +852,7 @@ __global__ void __launch_bounds__(T, 1) pn_dense_cta_kernel(const __grid_constan
         __syncthreads();
         qr_blocked<NB>(M, ldM, W2, ldM, Dn, QR_TOPTRI_BOTFULL, Dn, qs);
         if (FIX) {
-          solve_upper_blocked(M, W2, M + Dn, W2, X, Dn, Dn, Dn, smem);
+          solve_upper_blocked(M, W2, M + Dn, W2, X, Dn, Dn, Dn);
           for (size_t e = tid; e < MAT; e += T) {
             const int r = (int)(e / Dn), c = (int)(e - (size_t)r * Dn);
             GnT[e] = (pv[c] * X[e]) * pinvv[r];
@@ -756,13 +866,13 @@ __global__ void __launch_bounds__(T, 1) pn_dense_cta_kernel(const __grid_constan
           }
           __syncthreads();
           // merge with the running conditional (App. A.4), transposed storage
-          gemm<false>(GmT, Dn, GnT, Dn, false, S_GT, Dn, Dn, Dn, Dn, nullptr, 0, smem);
+          gemm<false>(GmT, Dn, GnT, Dn, false, S_GT, Dn, Dn, Dn, Dn, nullptr, 0);
           for (int i = tid; i < Dn; i += T) {
             double acc = S_g[i];
             for (int k = 0; k < Dn; ++k) acc = fma(S_GT[(size_t)k * Dn + i], gn[k], acc);
             gm[i] = acc;
           }
-          gemm<false>(M2, Dn, LnT, Dn, false, S_GT, Dn, Dn, Dn, Dn, nullptr, 0, smem);
+          gemm<false>(M2, Dn, LnT, Dn, false, S_GT, Dn, Dn, Dn, Dn, nullptr, 0);
           for (size_t e = tid; e < MAT; e += T) M2[MAT + e] = S_LamU[e];
           __syncthreads();
           qr_blocked<NB>(M2, Dn, W2, Dn, Dn, QR_TOPFULL_BOTTRI, Dn, qs);
@@ -789,11 +899,11 @@ __global__ void __launch_bounds__(T, 1) pn_dense_cta_kernel(const __grid_constan
         __syncthreads();
         qr_blocked<NB>(Rm, d, Dn, d, d, QR_FULL, 0, qs);
         // Wt[l][i] = sum_j L_ext[i][j] HL[l][j] = sum_j HLt[j][l] U_ext[j][i]
-        gemm<false>(Wt, Dn, HLt, d, true, U_ext, Dn, d, Dn, Dn, nullptr, 0, smem);
+        gemm<false>(Wt, Dn, HLt, d, true, U_ext, Dn, d, Dn, Dn, nullptr, 0);
         solve_upper_transposed_cols(Rm, d, Wt, Dn, Yt, Dn, d, Dn);
         solve_upper_cols(Rm, d, Yt, Dn, gainT, Dn, d, Dn);
         // Mc = L_ext^T - HL^T gain^T = U_ext - HLt gainT
-        gemm<true>(Mc, Dn, HLt, d, false, gainT, Dn, Dn, Dn, d, U_ext, Dn, smem);
+        gemm<true>(Mc, Dn, HLt, d, false, gainT, Dn, Dn, Dn, d, U_ext, Dn);
         qr_blocked<NB>(Mc, Dn, Dn, Dn, Dn, QR_FULL, 0, qs);
         for (int i = tid; i < Dn; i += T) {
           double acc = m_ext[i];
@@ -982,16 +1092,7 @@ __global__ void __launch_bounds__(T, 1) pn_dense_cta_smooth_kernel(const CtaSmoo
   const size_t MAT = (size_t)Dn * Dn, SLOT = slot_doubles(Dn, FIX), BW = 2 * MAT + Dn;
   extern __shared__ double smem[];
   QrSmem<NB> qs;
-  {
-    const int panel = QrSmem<NB>::panel_doubles(Dn + NB);
-    double* sp = smem + (panel > GEMM_SMEM ? panel : GEMM_SMEM);
-    qs.P = smem;
-    qs.Tm = sp;       sp += NB * NB;
-    qs.red = sp;      sp += WARPS * NB;
-    qs.v0 = sp;       sp += NB;
-    qs.beta = sp;     sp += NB;
-    qs.wy = sp;
-  }
+  qs.layout(Dn + NB);
   double* sc = a.scratch + (size_t)blockIdx.x * smooth_scratch_doubles(Dn);
   double* m = sc;          double* mo = m + Dn;
   double* U = mo + Dn;     double* M2 = U + MAT;
@@ -1009,7 +1110,7 @@ __global__ void __launch_bounds__(T, 1) pn_dense_cta_smooth_kernel(const CtaSmoo
         mo[i] = acc;
       }
       // M2 top = (G L)^T = U GT
-      gemm<false>(M2, Dn, U, Dn, false, GT, Dn, Dn, Dn, Dn, nullptr, 0, smem);
+      gemm<false>(M2, Dn, U, Dn, false, GT, Dn, Dn, Dn, Dn, nullptr, 0);
       for (size_t e = tid; e < MAT; e += T) M2[MAT + e] = LamU[e];
       __syncthreads();
       qr_blocked<NB>(M2, Dn, 2 * Dn, Dn, Dn, QR_TOPFULL_BOTTRI, Dn, qs);

@@ -15,27 +15,18 @@ template <int NB>
 __global__ void __launch_bounds__(T, 1) selftest_qr_kernel(double* M, int ld, int rows, int cols, int ncols, int shape, int ntop) {
   extern __shared__ double smem[];
   QrSmem<NB> qs;
-  const int panel = QrSmem<NB>::panel_doubles(rows + NB);
-  double* sp = smem + (panel > GEMM_SMEM ? panel : GEMM_SMEM);
-  qs.P = smem;
-  qs.Tm = sp;   sp += NB * NB;
-  qs.red = sp;  sp += WARPS * NB;
-  qs.v0 = sp;   sp += NB;
-  qs.beta = sp; sp += NB;
-  qs.wy = sp;
+  qs.layout(rows + NB);
   qr_blocked<NB>(M, ld, rows, cols, ncols, shape, ntop, qs);
 }
 __global__ void __launch_bounds__(T, 1) selftest_gemm_kernel(double* C, int ldc, const double* A, int lda, int a_kmajor, const double* B,
                                                              int ldb, int M, int N, int K, const double* C0, int ldc0, int neg) {
-  extern __shared__ double smem[];
   if (neg)
-    gemm<true>(C, ldc, A, lda, a_kmajor != 0, B, ldb, M, N, K, C0, ldc0, smem);
+    gemm<true>(C, ldc, A, lda, a_kmajor != 0, B, ldb, M, N, K, C0, ldc0);
   else
-    gemm<false>(C, ldc, A, lda, a_kmajor != 0, B, ldb, M, N, K, C0, ldc0, smem);
+    gemm<false>(C, ldc, A, lda, a_kmajor != 0, B, ldb, M, N, K, C0, ldc0);
 }
 __global__ void __launch_bounds__(T, 1) selftest_trsm_kernel(const double* R, int ldr, const double* B, int ldb, double* X, int ldx, int n, int c) {
-  extern __shared__ double smem[];
-  solve_upper_blocked(R, ldr, B, ldb, X, ldx, n, c, smem);
+  solve_upper_blocked(R, ldr, B, ldb, X, ldx, n, c);
 }
 }  // namespace cta
 }  // namespace pn

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "pn_coop_kernel.cuh"
 #include "pn_dense_cta_kernel.cuh"
 #include "pn_dense_kernel.cuh"
 #include "pn_dense_rows_kernel.cuh"
@@ -19,7 +20,8 @@ enum : int {
   FAMILY_DENSE = 3,       // warp per IVP, D x D factors in shared memory (dense, d > 1)
   FAMILY_WIDE = 4,        // CTA per IVP, isotropic, runtime dimension (Brusselator d = 2N up to 4096)
   FAMILY_DENSE_ROWS = 5,  // 16 or 32 lanes per IVP, register-resident Householder columns (dense, D <= 32)
-  FAMILY_DENSE_CTA = 6    // CTA per IVP, dense with a large runtime dimension, blocked QR on the FP64 tensor path
+  FAMILY_DENSE_CTA = 6,   // CTA per IVP, dense with a large runtime dimension, blocked QR on the FP64 tensor path
+  FAMILY_COOP = 7         // n lanes per IVP (scalar ODEs, small ensembles): columns of every QR spread over the lanes
 };
 inline bool family_is_dense(int family) { return family == FAMILY_DENSE || family == FAMILY_DENSE_ROWS; }
 
@@ -211,6 +213,31 @@ struct WideInstance {
   }
 };
 
+// scalar ODEs, small ensembles: n lanes per IVP (same slots / smoothing / sampling / likelihood kernels as the
+// thread-per-IVP family)
+template <class Prob, int NU, int STRAT, int THREADS>
+struct CoopInstance {
+  using Base = ScalarInstance<Prob, NU, STRAT, 1, 0, 128>;
+  static cudaError_t launch_solve(const SolveArgs& a, int grid, size_t smem, cudaStream_t s) {
+    pn_coop_kernel<Prob, NU, STRAT, THREADS><<<grid, THREADS, smem, s>>>(a);
+    return cudaGetLastError();
+  }
+  static KernelEntry entry() {
+    KernelEntry e = Base::entry();
+    using CL = CoopLayout<NU + 1>;
+    e.family = FAMILY_COOP;
+    e.group = NU + 1;
+    e.threads = THREADS;
+    e.smem_doubles = (THREADS / 32) * CL::G * CL::PER_GROUP + CL::STATE * THREADS;  // per CTA
+    e.ctx_doubles = 0;
+    e.solve_func_sliced = nullptr;
+    e.launch_solve_sliced = nullptr;
+    e.solve_func = (const void*)&pn_coop_kernel<Prob, NU, STRAT, THREADS>;
+    e.launch_solve = &launch_solve;
+    return e;
+  }
+};
+
 // dense factorisation with a large runtime dimension: CTA per IVP, blocked Householder QR + DMMA products
 template <class Prob, int NU, int STRAT, int NB>
 struct DenseCtaInstance {
@@ -273,6 +300,8 @@ struct Registrar {
   static ::pn::Registrar PN_CAT(pn_reg_, __COUNTER__)(::pn::DenseInstance<::pn::Prob, NU, STRAT, WARPS>::entry())
 #define PN_REGISTER_DENSE_ROWS(Prob, NU, STRAT, LANES, WARPS) \
   static ::pn::Registrar PN_CAT(pn_reg_, __COUNTER__)(::pn::DenseRowsInstance<::pn::Prob, NU, STRAT, LANES, WARPS>::entry())
+#define PN_REGISTER_COOP(Prob, NU, STRAT) \
+  static ::pn::Registrar PN_CAT(pn_reg_, __COUNTER__)(::pn::CoopInstance<::pn::Prob, NU, STRAT, 128>::entry())
 #define PN_REGISTER_DENSE_CTA(Prob, NU, STRAT, NB) \
   static ::pn::Registrar PN_CAT(pn_reg_, __COUNTER__)(::pn::DenseCtaInstance<::pn::cta::Prob, NU, STRAT, NB>::entry())
 #define PN_REGISTER_WIDE(Prob, NU, STRAT) \

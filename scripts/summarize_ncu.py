@@ -30,6 +30,8 @@ KEYS = [
     "launch__block_size", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
     "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
     "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active",
     "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
     "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed",
     "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed",
@@ -50,6 +52,8 @@ KEYS = [
     "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
 ]
 
 
