@@ -85,15 +85,17 @@ C4_TOLS = 10.0 ** -np.arange(3, 11)
 
 
 def c4_inputs(first, count, stride=1):
-    """Members of the seeded global Pleiades ensemble (seed 2): member b = (initial
-    condition b // 8, tolerance b % 8); positions perturbed by 0.01 N(0, I); rtol = 10 tol,
-    atol = 1e-3 rtol (experiments/3_workprec_harder/run_harder.py:45-47)."""
+    """Members of the seeded global Pleiades ensemble (seed 2): member b has tolerance index
+    (b // 8) % 8 and initial condition (b % 8) + 8 (b // 64) -- every run of 64 consecutive members is 8 initial
+    conditions x 8 tolerances, and ranks that own members r, r + G, ... (G = 1, 2, 4, 8) all see the same mix of
+    tolerances; positions perturbed by 0.01 N(0, I); rtol = 10 tol, atol = 1e-3 rtol
+    (experiments/3_workprec_harder/run_harder.py:45-47)."""
     total = first + stride * count
-    n_ic = (total + len(C4_TOLS) - 1) // len(C4_TOLS)
+    n_ic = 8 * ((total + 63) // 64)
     rng = np.random.default_rng(2)
     pos = PLEIADES_X + 0.01 * rng.standard_normal((n_ic, 14))
     idx = first + stride * np.arange(count)
-    ic, it = idx // len(C4_TOLS), idx % len(C4_TOLS)
+    ic, it = (idx % 8) + 8 * (idx // 64), (idx // 8) % 8
     u0 = np.stack([pos[ic], np.tile(PLEIADES_DX, (count, 1))], 1)
     rtol = 10.0 * C4_TOLS[it]
     tol = np.stack([1e-3 * rtol, rtol], 1)

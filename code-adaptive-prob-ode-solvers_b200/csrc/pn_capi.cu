@@ -177,7 +177,7 @@ __global__ void pn_order_scatter_kernel(const double* tol, long long B, unsigned
 }
 
 constexpr long long COOP_MAX_BATCH = 0;        // largest ensemble the cooperative scalar kernel is chosen for (0: opt-in only)
-constexpr long long DENSE_CTA_MAX_CTAS = 148;  // per-CTA scratch regions the workspace provides (SMs of a B200)
+constexpr long long DENSE_CTA_MAX_CTAS = 296;  // per-CTA scratch regions the workspace provides (2 per SM of a B200)
 static size_t dense_cta_smem_bytes(const KernelEntry* k, const pn_b200_desc* d) {
   const int Dn = (d->nu + 1) * d->d;
   return (k->smem_doubles == 32 ? cta::smem_doubles<32>(Dn) : cta::smem_doubles<16>(Dn)) * sizeof(double);
@@ -232,13 +232,19 @@ static int resolve(const pn_b200_desc* d, const KernelEntry** out) {
   if (!k && d->factorisation == PN_B200_DENSE && d->d > 1 && (d->d % 2) == 0) {
     k = find_kernel(FAMILY_DENSE_CTA, d->problem, d->nu, d->strategy, 0);
     if (k && dense_cta_smem_bytes(k, d) > WIDE_SMEM_LIMIT_BYTES) k = nullptr;  // D too large for one CTA's panel
+    // two CTAs per SM when their shared memory fits (+1 KB reserved per CTA) and there are members for them
+    if (k && 2 * (dense_cta_smem_bytes(k, d) + 1024) <= WIDE_SMEM_LIMIT_BYTES && d->batch > 148 && !getenv("PN_B200_DENSE_CTA_ONE")) {
+      const KernelEntry* k2 = find_kernel(FAMILY_DENSE_CTA, d->problem, d->nu, d->strategy, -2);
+      if (k2) k = k2;
+    }
   }
   // CTA-per-IVP wide family: isotropic EKF0 with a runtime dimension (Brusselator beyond the fixed sizes)
   if (!k && d->correction == PN_B200_TS0 && d->factorisation == PN_B200_ISOTROPIC && d->d >= 4 && d->d <= 4096 &&
       (d->d % 2) == 0)
     k = find_kernel(FAMILY_WIDE, d->problem, d->nu, d->strategy, 0);
-  if (k && k->group > 1 && k->family != FAMILY_COOP && (d->flags & PN_B200_FLAG_RECORD))
-    return fail(PN_B200_ERR_UNSUPPORTED, "trajectory recording is implemented for the thread-per-IVP kernels");
+  if (k && (d->flags & PN_B200_FLAG_RECORD) && k->family != FAMILY_SCALAR && k->family != FAMILY_COOP &&
+      k->family != FAMILY_GROUP_ISO && k->family != FAMILY_GROUP_BDIAG)
+    return fail(PN_B200_ERR_UNSUPPORTED, "trajectory recording is implemented for the thread-per-IVP and lane-per-dimension kernels");
   if (!k) {
     char buf[256];
     snprintf(buf, sizeof buf, "no kernel compiled for problem=%d nu=%d factorisation=%d correction=%d strategy=%d d=%d",

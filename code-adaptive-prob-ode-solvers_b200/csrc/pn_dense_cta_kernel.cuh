@@ -409,8 +409,8 @@ __device__ __noinline__ void qr_blocked(double* M, int ld, int rows, int cols, i
       double yb[2][NB / 4];
 #pragma unroll
       for (int kk = 0; kk < NB / 4; ++kk) {
-        yb[0][kk] = ys[(4 * kk + t) * 16 + 2 * g];
-        yb[1][kk] = ys[(4 * kk + t) * 16 + 2 * g + 1];
+        yb[0][kk] = -ys[(4 * kk + t) * 16 + 2 * g];  // C - V Y = C + V (-Y): fma(v, -y, c) == fma(-v, y, c) bit for bit
+        yb[1][kk] = -ys[(4 * kk + t) * 16 + 2 * g + 1];
       }
       // C <- C - V Y: chain over the panel columns, ascending, starting from C.  A lane owns 4 adjacent
       // columns c0 + 4t .. c0 + 4t + 3 of row g of every 8-row tile.
@@ -449,7 +449,7 @@ __device__ __noinline__ void qr_blocked(double* M, int ld, int rows, int cols, i
             const bool rv = r < h;
 #pragma unroll
             for (int kk = 0; kk < NB / 4; ++kk) {
-              const double a = rv ? -P[r * LDP + 4 * kk + t] : 0.0;
+              const double a = rv ? P[r * LDP + 4 * kk + t] : 0.0;
               dmma(xc[u][0], xc[u][2], a, yb[0][kk]);
               dmma(xc[u][1], xc[u][3], a, yb[1][kk]);
             }
@@ -642,8 +642,10 @@ __host__ __device__ inline size_t smem_doubles(int Dn) {
   return (size_t)(panel > GEMM_SMEM ? panel : GEMM_SMEM) + QrSmem<NB>::fixed_doubles() + 64;
 }
 
-template <class Prob, int NU, int STRAT, int NB>
-__global__ void __launch_bounds__(T, 1) pn_dense_cta_kernel(const __grid_constant__ SolveArgs a) {
+// MINB = 2: compiled for two resident CTAs per SM (128 registers; chosen by the host when two CTAs' shared
+// memory fits, i.e. for D up to ~400: twice the warps to hide the latency of the panel and the streamed tiles)
+template <class Prob, int NU, int STRAT, int NB, int MINB>
+__global__ void __launch_bounds__(T, MINB) pn_dense_cta_kernel(const __grid_constant__ SolveArgs a) {
   constexpr int N = NU + 1, Q = Prob::Q, P = (Prob::P > 0 ? Prob::P : 1);
   constexpr bool FIX = (STRAT == 1);
   constexpr double TIME_EPS = 10.0 * 2.220446049250313e-16;

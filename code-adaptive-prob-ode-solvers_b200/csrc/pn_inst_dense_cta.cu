@@ -2,9 +2,10 @@
 // dense EKF0 / EKF1, nu = 4 (BASELINE config 5), fixed-point smoother and filter.
 #include "pn_registry.h"
 namespace pn {
-PN_REGISTER_DENSE_CTA(BrusselatorRt, 4, 1, 16);
-PN_REGISTER_DENSE_CTA(BrusselatorRt, 4, 0, 16);
-PN_REGISTER_DENSE_CTA(BrusselatorRt, 2, 1, 16);
+PN_REGISTER_DENSE_CTA(BrusselatorRt, 4, 1, 16, 1);
+PN_REGISTER_DENSE_CTA(BrusselatorRt, 4, 1, 16, 2);
+PN_REGISTER_DENSE_CTA(BrusselatorRt, 4, 0, 16, 1);
+PN_REGISTER_DENSE_CTA(BrusselatorRt, 2, 1, 16, 1);
 }  // namespace pn
 
 // ---- test hooks (not part of the public header): the blocked primitives on caller-provided DEVICE

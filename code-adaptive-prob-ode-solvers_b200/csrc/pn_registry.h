@@ -239,10 +239,10 @@ struct CoopInstance {
 };
 
 // dense factorisation with a large runtime dimension: CTA per IVP, blocked Householder QR + DMMA products
-template <class Prob, int NU, int STRAT, int NB>
+template <class Prob, int NU, int STRAT, int NB, int MINB>
 struct DenseCtaInstance {
   static cudaError_t launch_solve(const SolveArgs& a, int grid, size_t smem, cudaStream_t s) {
-    cta::pn_dense_cta_kernel<Prob, NU, STRAT, NB><<<grid, cta::T, smem, s>>>(a);
+    cta::pn_dense_cta_kernel<Prob, NU, STRAT, NB, MINB><<<grid, cta::T, smem, s>>>(a);
     return cudaGetLastError();
   }
   static cudaError_t launch_smooth(const SmoothArgs& a, cudaStream_t s) {
@@ -271,14 +271,14 @@ struct DenseCtaInstance {
     e.nu = NU;
     e.strategy = STRAT;
     e.N = NU + 1;
-    e.D = 0;  // runtime dimension
+    e.D = (MINB == 2) ? -2 : 0;  // runtime dimension; -2 marks the two-CTAs-per-SM build
     e.Q = Prob::Q;
     e.P = Prob::P;
     e.slot_doubles = 0;  // runtime: cta::slot_doubles
     e.smem_doubles = NB; // runtime: cta::smem_doubles<NB>; this field carries the panel width
     e.threads = cta::T;
     e.has_jac = Prob::HAS_JAC;
-    e.solve_func = (const void*)&cta::pn_dense_cta_kernel<Prob, NU, STRAT, NB>;
+    e.solve_func = (const void*)&cta::pn_dense_cta_kernel<Prob, NU, STRAT, NB, MINB>;
     e.launch_solve = &launch_solve;
     e.launch_smooth = &launch_smooth;
     return e;
@@ -302,8 +302,8 @@ struct Registrar {
   static ::pn::Registrar PN_CAT(pn_reg_, __COUNTER__)(::pn::DenseRowsInstance<::pn::Prob, NU, STRAT, LANES, WARPS>::entry())
 #define PN_REGISTER_COOP(Prob, NU, STRAT) \
   static ::pn::Registrar PN_CAT(pn_reg_, __COUNTER__)(::pn::CoopInstance<::pn::Prob, NU, STRAT, 128>::entry())
-#define PN_REGISTER_DENSE_CTA(Prob, NU, STRAT, NB) \
-  static ::pn::Registrar PN_CAT(pn_reg_, __COUNTER__)(::pn::DenseCtaInstance<::pn::cta::Prob, NU, STRAT, NB>::entry())
+#define PN_REGISTER_DENSE_CTA(Prob, NU, STRAT, NB, MINB) \
+  static ::pn::Registrar PN_CAT(pn_reg_, __COUNTER__)(::pn::DenseCtaInstance<::pn::cta::Prob, NU, STRAT, NB, MINB>::entry())
 #define PN_REGISTER_WIDE(Prob, NU, STRAT) \
   static ::pn::Registrar PN_CAT(pn_reg_, __COUNTER__)(::pn::WideInstance<::pn::Prob, NU, STRAT, 128>::entry())
 #define PN_REGISTER_SCALAR_T(Prob, NU, STRAT, THREADS) \

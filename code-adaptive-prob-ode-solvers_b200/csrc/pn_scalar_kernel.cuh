@@ -589,11 +589,19 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
         n_acc = n_rej = n_att = 0;
         if (leader) a.n_accepted[b * a.K] = 0;
         emit_scale(0, sigma0);
-        if (GROUP == 1 && (a.flags & FLAG_RECORD)) {
-          a.traj_t[b] = t;
+        if (!WIDE && (a.flags & FLAG_RECORD)) {
+          // trajectory layout: traj_t / traj_std [cap][B], traj_u [cap][d][B]; a lane of a lane-per-dimension
+          // kernel writes its own dimension, the leader the time and (its) standard deviation
+          if (leader) {
+            a.traj_t[b] = t;
+            a.traj_std[b] = 0.0;
+          }
+          if (GROUP == 1) {
 #pragma unroll
-          for (int c = 0; c < D; ++c) a.traj_u[(long long)c * a.B + b] = SM(0, c);
-          a.traj_std[b] = 0.0;
+            for (int c = 0; c < D; ++c) a.traj_u[(long long)c * a.B + b] = SM(0, c);
+          } else if (real) {
+            a.traj_u[(long long)sub * a.B + b] = SM(0, 0);
+          }
         }
         if constexpr (WIDE) {
           if (!FIX) {  // filter: slot 0 holds the initial marginal (factor part zero)
@@ -1224,11 +1232,19 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
       for (int e = 0; e < Lay::MARG; ++e) dst[e] = s_state[e * THREADS + tid];
     };
     auto record = [&](double tt, const double (&mm)[N][D], const double (&LL)[N][N]) {
-      if (GROUP == 1 && (a.flags & FLAG_RECORD) && n_acc < a.traj_cap) {
-        a.traj_t[n_acc * VB + vb] = tt;
+      if (!WIDE && (a.flags & FLAG_RECORD) && n_acc < a.traj_cap) {
+        if (GROUP == 1) {
+          a.traj_t[n_acc * VB + vb] = tt;
 #pragma unroll
-        for (int c = 0; c < D; ++c) a.traj_u[(n_acc * D + c) * VB + vb] = mm[0][c];
-        a.traj_std[n_acc * VB + vb] = dsqrt(fma(LL[0][0], LL[0][0], 0.0));
+          for (int c = 0; c < D; ++c) a.traj_u[(n_acc * D + c) * VB + vb] = mm[0][c];
+          a.traj_std[n_acc * VB + vb] = dsqrt(fma(LL[0][0], LL[0][0], 0.0));
+        } else {
+          if (leader) {
+            a.traj_t[n_acc * a.B + b] = tt;
+            a.traj_std[n_acc * a.B + b] = dsqrt(fma(LL[0][0], LL[0][0], 0.0));
+          }
+          if (real) a.traj_u[(n_acc * DT + sub) * a.B + b] = mm[0][0];
+        }
       }
     };
     // exact hits on checkpoints by the committed state (m, L, running conditional): emit, reset
@@ -1433,7 +1449,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
         if (st != 0)
           for (long long kk = k_next; kk < a.K; ++kk) a.n_accepted[b * a.K + kk] = n_acc;
       }
-      if (GROUP == 1 && (a.flags & FLAG_RECORD)) a.traj_len[b] = (n_acc + 1 < a.traj_cap) ? (n_acc + 1) : a.traj_cap;
+      if (!WIDE && leader && (a.flags & FLAG_RECORD)) a.traj_len[b] = (n_acc + 1 < a.traj_cap) ? (n_acc + 1) : a.traj_cap;
       have = false;
     }
   }

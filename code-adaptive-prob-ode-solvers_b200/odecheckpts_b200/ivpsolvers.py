@@ -11,7 +11,7 @@ then ``[B, K, d]``.
 
 import numpy as np
 
-from .probdiffeq import ivpsolve, ivpsolvers, taylor
+from .probdiffeq import ivpsolve, ivpsolvers, stats, taylor
 
 
 def solve(method: str, vf, u0_like, /, save_at, *, dt0, atol, rtol, ode_order=1, calibrate="dynamic",
@@ -60,17 +60,12 @@ def solve(method: str, vf, u0_like, /, save_at, *, dt0, atol, rtol, ode_order=1,
 
 
 def solve_via_interpolate(method: str, vf, u0_like, /, save_at, *, dt0, atol, rtol, device=None):
-    """Drop-in for the reference's "textbook" comparator (src/odecheckpts/ivpsolvers.py:94-148):
-    smoother + save-every-step on [save_at[0] - 1e-6, save_at[-1] + 1e-6], then
-    ``stats.offgrid_marginals_searchsorted`` at ``save_at``.
-
-    The posterior it evaluates at ``save_at`` is the SAME Gaussian the fixed-point smoother carries
-    to its checkpoints (that equivalence is the point of the reference's paper), so this routine
-    runs the checkpoint solver on the same epsilon-extended interval with ``save_at`` as interior
-    checkpoints and returns those rows: same steps, same smoothed means, O(K) instead of O(#steps)
-    memory.  ``aux["u0_solve"]`` is the accepted-step solution the experiments use to report the
-    grid length (``length_of_longest_vector``, run_simple.py:200); it comes from a second,
-    filter-only launch that records every accepted step of the identical forward pass."""
+    """The reference's "textbook" comparator (src/odecheckpts/ivpsolvers.py:94-148), same construction:
+    ``strategy_smoother`` + ``solve_adaptive_save_every_step`` on [save_at[0] - 1e-6, save_at[-1] + 1e-6], then
+    ``stats.offgrid_marginals_searchsorted`` at ``save_at``.  Memory grows with the number of accepted steps
+    (one backward conditional per step in device memory): this is the O(#steps) route the checkpoint solver
+    ``solve`` replaces, kept so that the paper's memory / run-time comparison can be regenerated.  The two
+    routes evaluate the same posterior; they agree to rounding (tests/test_gpu_api.py)."""
     small_value = 1e-6
     num_derivatives = int(method[-1])
     if method[:3] == "ts0":
@@ -78,12 +73,10 @@ def solve_via_interpolate(method: str, vf, u0_like, /, save_at, *, dt0, atol, rt
     else:
         raise ValueError
     ibm = ivpsolvers.prior_ibm(num_derivatives=num_derivatives)
-    strategy = ivpsolvers.strategy_fixedpoint(ibm, correction)
+    strategy = ivpsolvers.strategy_smoother(ibm, correction)
     solver = ivpsolvers.solver_dynamic(strategy)
     control = ivpsolve.control_proportional_integral()
     asolver = ivpsolve.adaptive(solver, atol=atol, rtol=rtol, control=control)
-    solver_filter = ivpsolvers.solver_dynamic(ivpsolvers.strategy_filter(ibm, correction))
-    asolver_filter = ivpsolve.adaptive(solver_filter, atol=atol, rtol=rtol, control=control)
 
     def solve_(u0: tuple, p, output_scale=1.0):
         if not isinstance(u0, tuple):
@@ -92,19 +85,16 @@ def solve_via_interpolate(method: str, vf, u0_like, /, save_at, *, dt0, atol, rt
         def vf_wrapped(*y, t):
             return vf(*y, t=t, p=p)
 
-        grid = np.concatenate([[save_at[0] - small_value], np.asarray(save_at, dtype=np.float64), [save_at[-1] + small_value]])
         tcoeffs = taylor.odejet_padded_scan(vf_wrapped, u0, num=num_derivatives)
         init = solver.initial_condition(tcoeffs, output_scale=output_scale)
-        sol = ivpsolve.solve_adaptive_save_at(
-            vf_wrapped, init, save_at=grid, dt0=dt0, adaptive_solver=asolver, factorisation="isotropic", device=device
-        )
-        init_f = solver_filter.initial_condition(tcoeffs, output_scale=output_scale)
-        every = ivpsolve.solve_adaptive_save_every_step(
-            vf_wrapped, init_f, t0=grid[0], t1=grid[-1], dt0=dt0, adaptive_solver=asolver_filter,
+        sol = ivpsolve.solve_adaptive_save_every_step(
+            vf_wrapped, init,
+            # small perturbation so that all save_at values are in the interior of the domain (ivpsolvers.py:136-140)
+            t0=save_at[0] - small_value, t1=save_at[-1] + small_value, dt0=dt0, adaptive_solver=asolver,
             factorisation="isotropic", device=device,
         )  # fmt: skip
-        dense = sol.u[..., 1:-1, :]
-        return dense, {"solution": every, "u0_solve": every.u, "checkpoint_solution": sol}
+        dense, _ = stats.offgrid_marginals_searchsorted(ts=np.asarray(save_at, dtype=np.float64), solution=sol, solver=solver)
+        return dense, {"solution": sol, "u0_solve": sol.u}
 
     return solve_
 

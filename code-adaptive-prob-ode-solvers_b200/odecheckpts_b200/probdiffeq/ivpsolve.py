@@ -17,7 +17,7 @@ import numpy as np
 from .. import _cabi
 from ..ivps import resolve_vector_field
 from . import impl as _impl
-from .ivpsolvers import InitialCondition, Solver
+from .ivpsolvers import InitialCondition, Solver, Strategy
 from .stats import MarkovSeq, Normal
 
 
@@ -133,6 +133,8 @@ def _stack_members(inits, params, tol, output_scale, num_params):
 
 def _make_desc(field, nu, fact, solver, atol, rtol, control, dt0, B, K, flags=0, traj_capacity=0, max_attempts=0):
     strat = solver.strategy
+    if strat.name == "smoother":
+        raise ValueError("strategy_smoother is served by solve_adaptive_save_every_step + stats.offgrid_marginals_searchsorted")
     if strat.prior.num_derivatives != nu:
         raise ValueError(
             f"prior has num_derivatives={strat.prior.num_derivatives} but the Taylor coefficients carry nu={nu}"
@@ -219,11 +221,50 @@ def solve_adaptive_terminal_values(vf, initial_condition, t0, t1, adaptive_solve
                     num_steps=sol.num_steps[..., -1], num_rejected=sol.num_rejected, status=sol.status)  # fmt: skip
 
 
+def _with_strategy(adaptive_solver, name):
+    st = adaptive_solver.solver.strategy
+    solver = Solver(Strategy(name, st.prior, st.correction), adaptive_solver.solver.calibration)
+    return AdaptiveSolver(solver, adaptive_solver.atol, adaptive_solver.rtol, adaptive_solver.control)
+
+
+def _solve_on_checkpoints(ctx, checkpoints):
+    """Smoother context -> fixed-point solve with `checkpoints` (a superset of the accepted grid) as save_at."""
+    return solve_adaptive_save_at(ctx["vf"], ctx["init"], checkpoints, _with_strategy(ctx["adaptive_solver"], "fixedpoint"),
+                                  ctx["dt0"], factorisation=ctx["factorisation"], return_marginals=True, device=ctx["device"])  # fmt: skip
+
+
+def _solve_smoother_every_step(vf, initial_condition, t0, t1, adaptive_solver, dt0, factorisation, max_steps, device):
+    """strategy_smoother + solve_adaptive_save_every_step (src/odecheckpts/ivpsolvers.py:133-142): the textbook
+    O(#steps) smoother.  Pass 1 (filter kernel, trajectory recording) finds the accepted grid; pass 2 runs
+    the fixed-point kernel with EVERY accepted grid point as a checkpoint: each is hit exactly, so the running
+    backward conditional is emitted and reset at every step -- the workspace then holds one un-merged
+    conditional per accepted step (the smoother's posterior, #steps x slot bytes of device memory) and the
+    backward sweep marginalises through all of them.  Single IVP (the members of an ensemble have different
+    grids; loop over them)."""
+    every = solve_adaptive_save_every_step(vf, initial_condition, t0, t1, _with_strategy(adaptive_solver, "filter"), dt0,
+                                           factorisation=factorisation, max_steps=max_steps, device=device)  # fmt: skip
+    if np.ndim(every.t) != 1:
+        raise NotImplementedError("strategy_smoother solves one IVP per call (every member has its own grid)")
+    grid = np.asarray(every.t.detach().cpu() if _is_torch(every.t) else every.t, dtype=np.float64)
+    ctx = dict(vf=vf, init=initial_condition, adaptive_solver=adaptive_solver, solver=adaptive_solver.solver, dt0=dt0,
+               factorisation=factorisation, device=device, grid=grid)  # fmt: skip
+    sol = _solve_on_checkpoints(ctx, grid)
+    if int(np.asarray(sol.num_steps if not _is_torch(sol.num_steps) else sol.num_steps.cpu())[-1]) != len(grid) - 1:
+        raise RuntimeError("smoother pass did not reproduce the accepted grid of the filter pass")
+    post = MarkovSeq(sol.posterior.init, sol.posterior.marginals_all, None, ctx)
+    return Solution(t=sol.t, u=sol.u, u_std=sol.u_std, output_scale=sol.output_scale, marginals=sol.marginals,
+                    posterior=post, num_steps=len(grid) - 1, num_rejected=every.num_rejected, status=sol.status)  # fmt: skip
+
+
 def solve_adaptive_save_every_step(vf, initial_condition, t0, t1, adaptive_solver, dt0, *, factorisation=None,
                                    max_steps=1 << 16, device=None):  # fmt: skip
     """vdp.py:77-79: every accepted state is recorded; the last grid point is t1 (interpolated).
-    Implemented for the filter strategy (what the reference uses it with).  Unbatched results are
-    trimmed to the accepted grid; ensembles return padded arrays plus `num_steps`."""
+    Filter strategy: the recorded filter solution (what vdp.py uses).  Smoother strategy
+    (src/odecheckpts/ivpsolvers.py:133-142): the smoothed solution at every accepted grid point plus the
+    per-step backward conditionals (see _solve_smoother_every_step).  Unbatched results are trimmed to the
+    accepted grid; ensembles (filter only) return padded arrays plus `num_steps`."""
+    if adaptive_solver.solver.strategy.name == "smoother":
+        return _solve_smoother_every_step(vf, initial_condition, t0, t1, adaptive_solver, dt0, factorisation, max_steps, device)
     desc, out, _, batched = _solve(vf, initial_condition, np.asarray([t0, t1], dtype=np.float64), adaptive_solver, dt0,
                                    factorisation=factorisation, return_marginals=False, tol=None, max_attempts=0,
                                    device=device, flags=_cabi.FLAG_RECORD, traj_capacity=int(max_steps))  # fmt: skip

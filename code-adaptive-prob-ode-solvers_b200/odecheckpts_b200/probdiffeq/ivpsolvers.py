@@ -17,7 +17,7 @@ class Correction(NamedTuple):
 
 
 class Strategy(NamedTuple):
-    name: str  # "filter" | "fixedpoint"
+    name: str  # "filter" | "fixedpoint" | "smoother"
     prior: Prior
     correction: Correction
 
@@ -64,10 +64,11 @@ def strategy_fixedpoint(prior, correction):
 
 
 def strategy_smoother(prior, correction):
-    raise NotImplementedError(
-        "strategy_smoother (O(#steps) memory; src/odecheckpts/ivpsolvers.py:94-148) is the comparator the "
-        "checkpoint solver replaces and is outside the accelerated path; use strategy_fixedpoint"
-    )
+    """The textbook smoother (src/odecheckpts/ivpsolvers.py:112; experiments/4_brusselator/run.py:103): one
+    backward conditional is kept PER ACCEPTED STEP -- O(#steps) memory, the comparator the fixed-point
+    strategy replaces.  Served by ``ivpsolve.solve_adaptive_save_every_step`` (which stores the per-step
+    conditionals in device memory) and ``stats.offgrid_marginals_searchsorted``."""
+    return Strategy("smoother", prior, correction)
 
 
 def solver(strategy):

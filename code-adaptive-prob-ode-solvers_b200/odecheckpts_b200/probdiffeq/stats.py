@@ -17,6 +17,7 @@ class MarkovSeq(NamedTuple):
     init: Normal          # marginals at checkpoints 1..K-1 (init.mean[-1] = terminal)
     marginals_all: Normal  # smoothed marginals at checkpoints 0..K-1
     handle: object = None  # (descriptor, device workspace, device status) when the solve kept its conditionals
+    context: object = None  # smoother solutions: what stats.offgrid_marginals_searchsorted needs to evaluate off the grid
 
 
 def markov_select_terminal(posterior):
@@ -85,3 +86,32 @@ def log_marginal_likelihood(u, /, *, standard_deviation, posterior):
     if as_numpy:
         out = out.cpu().numpy()
     return out if batched else out[0]
+
+
+def offgrid_marginals_searchsorted(*, ts, solution, solver):
+    """Marginals of a SMOOTHER solution at off-grid times ``ts`` (src/odecheckpts/ivpsolvers.py:117,144):
+    for t in (t_i, t_{i+1}) the filter marginal at t_i is extrapolated to t, the backward conditional
+    t_{i+1} -> t comes from extrapolating on to t_{i+1}, and the smoothed marginal at t_{i+1} is pulled back
+    through it.  On the device this is the checkpoint machinery of the solver kernel with the accepted grid
+    AND ``ts`` as checkpoints: grid points are hit exactly (one un-merged conditional per step, exactly the
+    smoother's posterior), the off-grid times are interpolated inside their step, and the backward sweep
+    marginalises through all of them.  Returns ``(u [len(ts), d], Normal marginals)`` like probdiffeq."""
+    post = solution.posterior
+    if not isinstance(post, MarkovSeq) or post.context is None:
+        raise TypeError("expected a solution of solve_adaptive_save_every_step with strategy_smoother")
+    import numpy as np
+
+    from . import ivpsolve
+
+    ctx = post.context
+    if solver is not ctx["solver"]:
+        raise ValueError("offgrid_marginals_searchsorted: `solver` is not the solver the solution was computed with")
+    ts = np.asarray(ts, dtype=np.float64)
+    grid = ctx["grid"]
+    if ts.ndim != 1 or ts.min() <= grid[0] or ts.max() >= grid[-1]:
+        raise ValueError("ts must lie strictly inside the solution's time interval")
+    union = np.union1d(grid, ts)
+    sol = ivpsolve._solve_on_checkpoints(ctx, union)
+    idx = np.searchsorted(union, ts)
+    marg = Normal(sol.marginals.mean[idx], sol.marginals.cholesky[idx])
+    return sol.u[idx], marg

@@ -233,3 +233,51 @@ def test_two_solvers_return_the_same_solution(oracle, m0, m1, which):
     assert "u0_solve" in aux1.keys()
     assert "u0_solve" in aux2.keys()
     assert np.allclose(solution1, solution2, atol=np.sqrt(atol), rtol=np.sqrt(rtol))
+
+
+def test_textbook_smoother_route_and_checkpoint_solver_evaluate_the_same_posterior(oracle):
+    """strategy_smoother + solve_adaptive_save_every_step + offgrid_marginals_searchsorted
+    (src/odecheckpts/ivpsolvers.py:94-148, experiments/4_brusselator/run.py:102-117): one backward conditional
+    per accepted step, O(#steps) memory.  (a) it is bit-identical to the oracle run with the accepted grid and
+    save_at as checkpoints; (b) it agrees with the O(K) fixed-point checkpoint solver to rounding -- the
+    equivalence the reference's paper is about; (c) its memory grows with the number of steps."""
+    from odecheckpts_b200 import ivps, ivpsolvers
+    from odecheckpts_b200.probdiffeq import ivpsolve, stats, taylor
+    from odecheckpts_b200.probdiffeq import ivpsolvers as pdi
+
+    vf, u0, tspan, params = ivps.rigid_body(time_span=(0.0, 10.0))
+    save_at = np.linspace(0.0, 10.0, 6)
+    tol = 1e-5
+    dense, aux = ivpsolvers.solve_via_interpolate("ts0-4", vf, u0[0], save_at=save_at, dt0=0.1, atol=tol, rtol=tol)(u0, params)
+    sol = aux["solution"]
+    n_grid = len(sol.t)
+    assert dense.shape == (6, 3) and n_grid > 50 and aux["u0_solve"].shape == (n_grid, 3)
+    # (b) same posterior by two routes: the fixed-point solver on the same interval keeps K + 2 merged conditionals
+    ext = np.concatenate([[sol.t[0]], save_at, [sol.t[-1]]])
+    ckpt = ivpsolve._solve_on_checkpoints(sol.posterior.context, ext)
+    assert int(ckpt.num_steps[-1]) == n_grid - 1
+    np.testing.assert_allclose(dense, ckpt.u[1:-1], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(ivpsolvers.solve("ts0-4", vf, u0[0], save_at=save_at, dt0=0.1, atol=tol, rtol=tol)(u0, params)[0],
+                               dense, atol=1e-4)  # the reference's own pair of routines (intervals differ by 1e-6)
+    # (a) oracle: adaptive fixed-point solve on [t0 - 1e-6, t1 + 1e-6] with grid + save_at as checkpoints
+    grid = np.asarray(sol.t)
+    union = np.union1d(grid, save_at)
+    cfg = oracle.make_config("rigid_body", 3, 4, 1, atol=tol, rtol=tol, dt0=0.1, num_params=3)
+    ora = oracle.solve_save_at(cfg, u0[0][None], params, union)
+    assert ora["status"] == 0 and ora["n_accepted"][-1] == n_grid - 1
+    np.testing.assert_array_equal(dense, ora["u"][np.searchsorted(union, save_at)])
+    ora_grid = oracle.solve_save_at(cfg, u0[0][None], params, grid)
+    np.testing.assert_array_equal(np.asarray(sol.u), ora_grid["u"])
+    # (c) the builder vocabulary the scripts use, and the memory the smoother holds on the device
+    strategy = pdi.strategy_smoother(pdi.prior_ibm(num_derivatives=4), pdi.correction_ts0())
+    solver = pdi.solver_dynamic(strategy)
+    asolver = ivpsolve.adaptive(solver, atol=tol, rtol=tol, control=ivpsolve.control_proportional_integral())
+    tcoeffs = taylor.odejet_padded_scan(lambda y, t: vf(y, t=t, p=params), u0, num=4)
+    init = solver.initial_condition(tcoeffs, output_scale=1.0)
+    s2 = ivpsolve.solve_adaptive_save_every_step(lambda y, t: vf(y, t=t, p=params), init, t0=0.0, t1=10.0, dt0=0.1,
+                                                 adaptive_solver=asolver, factorisation="isotropic")  # fmt: skip
+    u_off, marg = stats.offgrid_marginals_searchsorted(ts=np.array([2.5, 7.25]), solution=s2, solver=solver)
+    assert u_off.shape == (2, 3) and marg.mean.shape == (2, 5, 3)
+    truth = __import__("scipy.integrate").integrate.solve_ivp(lambda t, y: vf(y, t=t, p=params), (0.0, 10.0), u0[0], t_eval=[2.5, 7.25],
+                                                              method="DOP853", atol=1e-12, rtol=1e-12).y.T  # fmt: skip
+    np.testing.assert_allclose(u_off, truth, atol=1e-3)

@@ -64,7 +64,7 @@ def test_reported_standard_deviations_are_calibrated(cabi):
     y0 = np.array([1.0, 0.0, 0.9])
     truth = solve_ivp(lambda t, y: [a * y[1] * y[2], b * y[0] * y[2], c * y[0] * y[1]], (0, 10), y0, method="DOP853",
                       t_eval=save_at, rtol=1e-13, atol=1e-13).y.T  # fmt: skip
-    for fact, corr, nu in (("isotropic", "ts0", 4), ("dense", "ts1", 4), ("blockdiag", "ts0", 3)):
+    for fact, corr, nu in (("isotropic", "ts0", 4), ("dense", "ts1", 4), ("blockdiag", "ts0", 4)):
         for tol in (1e-4, 1e-7):
             desc = cabi.Desc(1, 3, nu, 1, cabi.FACTORISATIONS[fact], cabi.CORRECTIONS[corr], 1, 1, tol, tol, 0.1,
                              0.95, 0.2, 10.0, 0.3, 0.4, 1, len(save_at), 0, 3, 0, 0)  # fmt: skip
