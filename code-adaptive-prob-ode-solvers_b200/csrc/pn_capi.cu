@@ -132,6 +132,7 @@ struct Plan {
   size_t ws_slice = 0;     // time-sliced scheduling: ready queues [G][B] + control words + parked states [B][ctx]
   int slice_shift = 0;     // queue group of a member = (k_next - 1) >> slice_shift, G <= 63 groups
   size_t ws_queue = 0;     // ... of which the ready queues (set to -1 before every launch)
+  size_t ws_mle = 0;       // solver_mle: [B] final calibration factors
 };
 
 // ---------------------------------------------------------------------------------------
@@ -176,6 +177,7 @@ __global__ void pn_order_scatter_kernel(const double* tol, long long B, unsigned
   if (i < B) order[atomicAdd(&cursor[order_bucket(tol[2 * i], tol[2 * i + 1])], 1u)] = i;
 }
 
+constexpr long long WIDE_WARP_MIN_BATCH = 592;  // CTA-per-IVP isotropic family: one warp per IVP from four members per SM on
 constexpr long long COOP_MAX_BATCH = 0;        // largest ensemble the cooperative scalar kernel is chosen for (0: opt-in only)
 constexpr long long DENSE_CTA_MAX_CTAS = 296;  // per-CTA scratch regions the workspace provides (2 per SM of a B200)
 static size_t dense_cta_smem_bytes(const KernelEntry* k, const pn_b200_desc* d) {
@@ -191,7 +193,7 @@ static int resolve(const pn_b200_desc* d, const KernelEntry** out) {
     return fail(PN_B200_ERR_ARGUMENT, "unknown strategy");
   if (d->correction != PN_B200_TS0 && d->correction != PN_B200_TS1)
     return fail(PN_B200_ERR_ARGUMENT, "unknown correction");
-  if (d->calibration != PN_B200_CALIB_NONE && d->calibration != PN_B200_CALIB_DYNAMIC)
+  if (d->calibration != PN_B200_CALIB_NONE && d->calibration != PN_B200_CALIB_DYNAMIC && d->calibration != PN_B200_CALIB_MLE)
     return fail(PN_B200_ERR_ARGUMENT, "unknown calibration");
   if ((d->flags & PN_B200_FLAG_RECORD) && d->strategy != PN_B200_FILTER)
     return fail(PN_B200_ERR_UNSUPPORTED, "trajectory recording is implemented for the filter strategy");
@@ -207,7 +209,7 @@ static int resolve(const pn_b200_desc* d, const KernelEntry** out) {
   // n lanes removes arithmetic from the lanes but adds exchanges to the chain, and ends up 15-60 % SLOWER than
   // the thread-per-IVP kernel at every ensemble size (1 member: 81 vs 70 ms; 8,192: 126 vs 78 ms).  It stays
   // in the tree as a bit-identical cross-check and for experiments: PN_B200_COOP_MAX_BATCH=<members>.
-  if (k && d->d == 1 && !getenv("PN_B200_NO_COOP")) {
+  if (k && d->d == 1 && d->calibration != PN_B200_CALIB_MLE && !getenv("PN_B200_NO_COOP")) {
     long long coop_max = COOP_MAX_BATCH;
     if (const char* e = getenv("PN_B200_COOP_MAX_BATCH")) coop_max = atoll(e);
     if (d->batch <= coop_max) {
@@ -241,7 +243,16 @@ static int resolve(const pn_b200_desc* d, const KernelEntry** out) {
   // CTA-per-IVP wide family: isotropic EKF0 with a runtime dimension (Brusselator beyond the fixed sizes)
   if (!k && d->correction == PN_B200_TS0 && d->factorisation == PN_B200_ISOTROPIC && d->d >= 4 && d->d <= 4096 &&
       (d->d % 2) == 0)
+  {
     k = find_kernel(FAMILY_WIDE, d->problem, d->nu, d->strategy, 0);
+    // large ensembles: one warp per IVP (WIDE_WARP_MIN_BATCH members = four per SM; PN_B200_WIDE_WARP=0/1 forces)
+    const char* ww = getenv("PN_B200_WIDE_WARP");
+    const bool want_warp = ww ? (ww[0] == '1') : (d->batch >= WIDE_WARP_MIN_BATCH);
+    if (k && want_warp) {
+      const KernelEntry* k32 = find_kernel(FAMILY_WIDE, d->problem, d->nu, d->strategy, -32);
+      if (k32) k = k32;
+    }
+  }
   if (k && (d->flags & PN_B200_FLAG_RECORD) && k->family != FAMILY_SCALAR && k->family != FAMILY_COOP &&
       k->family != FAMILY_GROUP_ISO && k->family != FAMILY_GROUP_BDIAG)
     return fail(PN_B200_ERR_UNSUPPORTED, "trajectory recording is implemented for the thread-per-IVP and lane-per-dimension kernels");
@@ -251,6 +262,8 @@ static int resolve(const pn_b200_desc* d, const KernelEntry** out) {
              d->problem, d->nu, d->factorisation, d->correction, d->strategy, d->d);
     return fail(PN_B200_ERR_UNSUPPORTED, buf);
   }
+  if (d->calibration == PN_B200_CALIB_MLE && k->family != FAMILY_SCALAR)
+    return fail(PN_B200_ERR_UNSUPPORTED, "solver_mle (running quasi-MLE calibration) is implemented for the thread-per-IVP kernels");
   if (k->Q != d->ode_order) return fail(PN_B200_ERR_ARGUMENT, "ode_order does not match the problem");
   if (d->correction == PN_B200_TS1 && !k->has_jac) return fail(PN_B200_ERR_UNSUPPORTED, "problem has no compiled Jacobian");
   if (d->num_params < 0 || d->num_params > (k->P > 0 ? k->P : 0)) return fail(PN_B200_ERR_ARGUMENT, "num_params exceeds the problem's parameter count");
@@ -290,9 +303,11 @@ static int make_plan(const pn_b200_desc* d, Plan* p, bool need_device) {
     p->ws_cond = (size_t)d->batch * d->num_save_at * cta::slot_doubles(Dn, d->strategy == PN_B200_FIXEDPOINT) * sizeof(double);
     p->ws_wide = (size_t)ctas * cta::scratch_doubles(Dn, d->d, d->ode_order) * sizeof(double);
   }
+  if (d->calibration == PN_B200_CALIB_MLE) p->ws_mle = ((size_t)d->batch * sizeof(double) + 255) / 256 * 256;
   // time-sliced scheduling (pn_scalar_kernel.cuh: SolveArgs::slice): thread-per-IVP kernels, enough
   // checkpoints to slice at, bounded queue memory
   if (p->k->ctx_doubles > 0 && d->num_save_at >= SLICE_MIN_CHECKPOINTS && d->batch > 1 && d->batch < 0x7fffffffLL &&
+      d->calibration != PN_B200_CALIB_MLE &&  // (the parked context does not carry the running MLE sum)
       !(d->flags & (PN_B200_FLAG_RECORD | PN_B200_FLAG_FIXED_GRID))) {
     int shift = 0;
     while (((d->num_save_at - 2) >> shift) > 62) ++shift;
@@ -386,7 +401,7 @@ int pn_b200_supported(const pn_b200_desc* desc) {
 size_t pn_b200_workspace_bytes(const pn_b200_desc* desc) {
   Plan p;
   if (make_plan(desc, &p, false)) return 0;
-  return p.ws_ticket + p.ws_cond + p.ws_wide + p.ws_slice;
+  return p.ws_ticket + p.ws_cond + p.ws_wide + p.ws_slice + p.ws_mle;
 }
 
 int pn_b200_output_sizes(const pn_b200_desc* desc, pn_b200_sizes* sz) {
@@ -447,7 +462,7 @@ int pn_b200_solve_save_at(const pn_b200_desc* desc, const double* u0, const doub
   if (desc->num_params > 0 && !params) return fail(PN_B200_ERR_ARGUMENT, "params is null but num_params > 0");
   if ((desc->flags & PN_B200_FLAG_RECORD) && (!traj_t || !traj_u || !traj_std || !traj_len || desc->traj_capacity < 2))
     return fail(PN_B200_ERR_ARGUMENT, "trajectory recording needs traj buffers and traj_capacity >= 2");
-  if (!workspace || workspace_bytes < p.ws_ticket + p.ws_cond + p.ws_wide + p.ws_slice)
+  if (!workspace || workspace_bytes < p.ws_ticket + p.ws_cond + p.ws_wide + p.ws_slice + p.ws_mle)
     return fail(PN_B200_ERR_WORKSPACE, "workspace too small");
   cudaStream_t stream = (cudaStream_t)cuda_stream;
 
@@ -480,6 +495,7 @@ int pn_b200_solve_save_at(const pn_b200_desc* desc, const double* u0, const doub
   a.wide_smem_means = p.wide_smem_means;
   a.wide_mean = (double*)((char*)workspace + p.ws_ticket + p.ws_cond);
   a.out_scale = output_scale;
+  a.mle_scale = p.ws_mle ? (double*)((char*)workspace + p.ws_ticket + p.ws_cond + p.ws_wide + p.ws_slice) : nullptr;
   a.n_accepted = (long long*)n_accepted;
   a.n_rejected = (long long*)n_rejected;
   a.status = status;
@@ -554,6 +570,7 @@ int pn_b200_solve_save_at(const pn_b200_desc* desc, const double* u0, const doub
   s.wide_mean = a.wide_mean;
   s.wide_ctas = p.grid;
   s.cond = a.cond;
+  s.mle_scale = a.mle_scale;
   s.status = status;
   s.u = u;
   s.u_std = u_std;

@@ -3,3 +3,7 @@
 #include "pn_registry.h"
 PN_REGISTER_WIDE(BrusselatorWide, 4, 1);
 PN_REGISTER_WIDE(BrusselatorWide, 4, 0);
+// One warp per IVP: every thread of a CTA replicates the n x n factor arithmetic (it is the serial part of the
+// step), so a 128-thread CTA issues it four times per attempted step.  For ensembles with several members per
+// SM the 32-thread build issues it once and keeps up to eight members resident per SM instead of two.
+PN_REGISTER_WIDE_T(BrusselatorWide, 4, 1, 32);

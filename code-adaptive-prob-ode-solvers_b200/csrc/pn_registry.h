@@ -199,7 +199,7 @@ struct WideInstance {
     e.nu = NU;
     e.strategy = STRAT;
     e.N = NU + 1;
-    e.D = 0;  // runtime dimension
+    e.D = (THREADS == 128) ? 0 : -THREADS;  // runtime dimension; -32: the one-warp-per-IVP build for large ensembles
     e.Q = Prob::Q;
     e.P = Prob::P;
     e.slot_doubles = Lay::BW + Lay::NT;  // factor part of a slot; + 2 n d per slot and 3 n d per member at run time
@@ -306,6 +306,8 @@ struct Registrar {
   static ::pn::Registrar PN_CAT(pn_reg_, __COUNTER__)(::pn::DenseCtaInstance<::pn::cta::Prob, NU, STRAT, NB, MINB>::entry())
 #define PN_REGISTER_WIDE(Prob, NU, STRAT) \
   static ::pn::Registrar PN_CAT(pn_reg_, __COUNTER__)(::pn::WideInstance<::pn::Prob, NU, STRAT, 128>::entry())
+#define PN_REGISTER_WIDE_T(Prob, NU, STRAT, THREADS) \
+  static ::pn::Registrar PN_CAT(pn_reg_, __COUNTER__)(::pn::WideInstance<::pn::Prob, NU, STRAT, THREADS>::entry())
 #define PN_REGISTER_SCALAR_T(Prob, NU, STRAT, THREADS) \
   static ::pn::Registrar PN_CAT(pn_reg_, __COUNTER__)(::pn::ScalarInstance<::pn::Prob, NU, STRAT, 1, 0, THREADS>::entry())
 #define PN_REGISTER_GROUP_T(Prob, NU, STRAT, GROUP, BDIAG, THREADS) \

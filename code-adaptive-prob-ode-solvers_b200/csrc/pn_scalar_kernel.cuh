@@ -55,7 +55,7 @@ enum : int { FLAG_FIXED_GRID = 1, FLAG_RECORD = 2 };
 
 struct SolveArgs {
   int32_t correction;   // 0 ts0, 1 ts1 (D == 1 only)
-  int32_t calibration;  // 0 none, 1 dynamic
+  int32_t calibration;  // 0 none, 1 dynamic, 2 running quasi-MLE (solver_mle; thread-per-IVP kernels)
   int32_t flags;
   int32_t num_params;
   double atol, rtol, dt0;
@@ -93,6 +93,9 @@ struct SolveArgs {
   unsigned* sq;
   unsigned long long* sw;
   double* ctx;
+  // calibration == 2 (solver_mle): [B] the final quasi-MLE factor sqrt(mean over accepted steps of z^T S^-1 z / d)
+  // that the smoothing kernel applies to the marginal standard deviations / factors (nullable otherwise)
+  double* mle_scale;
   // nullable [B][K][S]: the output scale carried by every checkpoint (solution.output_scale);
   // S = d for the blockdiag factorisation (one scale per dimension), else 1
   double* out_scale;
@@ -440,6 +443,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
   double par[P];
   int mode = MODE_STEP;
   long long k_next = 1, n_acc = 0, n_rej = 0, n_att = 0;
+  double mle_ss = 0.0;  // solver_mle: sum over the accepted steps of z^T S^-1 z / d
   // utilisation statistics (per warp, flushed once at exit): loop iterations, lane-iterations with
   // work, lane-iterations spent on checkpoint interpolation
   unsigned long long stat_warp_iters = 0, stat_lane_iters = 0, stat_interp_iters = 0;
@@ -448,6 +452,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
   // solution.output_scale at checkpoint k: one value per IVP, one per dimension for blockdiag
   auto emit_scale = [&](long long k, double v) {
     if (a.out_scale) {
+      if (a.calibration == 2) v = sigma0 * ((n_acc > 0) ? dsqrt(mle_ss * rcp((double)n_acc)) : 1.0);  // running MLE
       if (BDIAG) {
         if (real) a.out_scale[(b * a.K + k) * DT + sub] = v;
       } else if (leader) {
@@ -587,6 +592,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
         mode = MODE_STEP;
         k_next = 1;
         n_acc = n_rej = n_att = 0;
+        mle_ss = 0.0;
         if (leader) a.n_accepted[b * a.K] = 0;
         emit_scale(0, sigma0);
         if (!WIDE && (a.flags & FLAG_RECORD)) {
@@ -771,6 +777,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
     }
     // local calibration + error estimate from the process noise
     double err, sigma;
+    double mle_zz = 0.0, mle_invS = 0.0;  // solver_mle: the two ingredients of z^T S^-1 z
     {
       double s2 = 0.0;
 #pragma unroll
@@ -791,6 +798,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
         zz = real ? fma(z[0], z[0], 0.0) : 0.0;
         if (!BDIAG) zz = group_sum<GROUP>(zz, gmask);
       }
+      mle_zz = zz;
       double sigma_hat = dsqrt(zz) * rcp(s);
       sigma_hat = BDIAG ? sigma_hat : sigma_hat * inv_sqrt_d;
       err = (fabs(dt) * sigma_hat) * s;
@@ -1030,6 +1038,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
         S = fma(acc, acc, S);
       }
       double invS = rcp(S);
+      mle_invS = invS;
 #pragma unroll
       for (int i = 0; i < N; ++i) {
         double acc = 0.0;
@@ -1323,6 +1332,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
             le_prev = le_now;
           }
           n_acc += 1;
+          if (GROUP == 1 && !WIDE && a.calibration == 2) mle_ss = mle_ss + (mle_zz * mle_invS) * (1.0 / (double)DT);
           const double t1 = fixed_grid ? t_ck : (t + dt);
           const bool overshoot = (k_next < a.K) && (t1 > t_ck + TIME_EPS);
           if (overshoot) {
@@ -1446,6 +1456,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
       if (leader) {
         a.n_rejected[b] = n_rej;
         a.status[b] = st;
+        if (a.mle_scale) a.mle_scale[b] = (a.calibration == 2 && n_acc > 0) ? dsqrt(mle_ss * rcp((double)n_acc)) : 1.0;
         if (st != 0)
           for (long long kk = k_next; kk < a.K; ++kk) a.n_accepted[b * a.K + kk] = n_acc;
       }

@@ -20,6 +20,7 @@ struct SmoothArgs {
   double* wide_mean;   // wide kernels: per-member mean scratch [B][3][n][d]; dense CTA kernels: per-CTA scratch
   long long wide_ctas; // dense CTA kernels: CTAs the scratch has room for
   const double* cond;  // [B*dv][K][SLOT]
+  const double* mle_scale;  // nullable [B]: solver_mle's final factor on the standard deviations / factors
   const int32_t* status;
   double* u;           // [B][K][D]
   double* u_std;       // [B][K][D]
@@ -124,9 +125,10 @@ __global__ void __launch_bounds__(128) pn_smooth_kernel(const SmoothArgs a) {
     marginalise_from_global<N, D>(m, L, a.cond + vb * a.K * SLOT, 1);
   }
   const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+  const double sc = a.mle_scale ? a.mle_scale[b] : 1.0;
   for (long long k = a.K - 1; k >= 0; --k) {
     if (!FIX) load_marg(a.cond + (vb * a.K + k) * SLOT);
-    const double sd = dsqrt(fma(L[0][0], L[0][0], 0.0));
+    const double sd = sc * dsqrt(fma(L[0][0], L[0][0], 0.0));
 #pragma unroll
     for (int c = 0; c < D; ++c) {
       a.u[(b * a.K + k) * dtot + cv * D + c] = ok ? m[0][c] : nanv;
@@ -143,7 +145,7 @@ __global__ void __launch_bounds__(128) pn_smooth_kernel(const SmoothArgs a) {
 #pragma unroll
       for (int i = 0; i < N; ++i)
 #pragma unroll
-        for (int j = 0; j < N; ++j) a.marg_chol[(blk * N + i) * N + j] = ok ? ((j <= i) ? L[i][j] : 0.0) : nanv;
+        for (int j = 0; j < N; ++j) a.marg_chol[(blk * N + i) * N + j] = ok ? ((j <= i) ? sc * L[i][j] : 0.0) : nanv;
     }
     if (k == 0) break;
     if (FIX) marginalise_from_global<N, D>(m, L, a.cond + (vb * a.K + k) * SLOT, 1);

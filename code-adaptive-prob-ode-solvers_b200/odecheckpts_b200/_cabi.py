@@ -24,7 +24,7 @@ PROBLEM_IDS = {
 FACTORISATIONS = {"isotropic": 0, "blockdiag": 1, "dense": 2}
 CORRECTIONS = {"ts0": 0, "ts1": 1}
 STRATEGIES = {"filter": 0, "fixedpoint": 1}
-CALIBRATIONS = {"none": 0, "dynamic": 1}
+CALIBRATIONS = {"none": 0, "dynamic": 1, "mle": 2}
 FLAG_FIXED_GRID = 1
 FLAG_RECORD = 2
 STATUS_OK, STATUS_NAN, STATUS_MAX_ATTEMPTS = 0, 1, 2

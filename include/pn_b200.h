@@ -41,7 +41,13 @@ enum {
 enum { PN_B200_ISOTROPIC = 0, PN_B200_BLOCKDIAG = 1, PN_B200_DENSE = 2 }; /* impl.select, ivpsolvers.py:33 */
 enum { PN_B200_TS0 = 0, PN_B200_TS1 = 1 };            /* correction_ts0/ts1, ivpsolvers.py:37; vdp.py:64 */
 enum { PN_B200_FILTER = 0, PN_B200_FIXEDPOINT = 1 };  /* strategy_*, ivpsolvers.py:43; vdp.py:65          */
-enum { PN_B200_CALIB_NONE = 0, PN_B200_CALIB_DYNAMIC = 1 }; /* solver / solver_dynamic, ivpsolvers.py:45-48 */
+enum {
+  PN_B200_CALIB_NONE = 0,    /* ivpsolvers.solver,         ivpsolvers.py:48 */
+  PN_B200_CALIB_DYNAMIC = 1, /* ivpsolvers.solver_dynamic, ivpsolvers.py:46 */
+  PN_B200_CALIB_MLE = 2      /* ivpsolvers.solver_mle (no call site in the reference): the solve uses output_scale0; the
+                                running quasi-MLE sqrt(mean over accepted steps of z^T S^-1 z / d) is reported in
+                                output_scale and its final value scales u_std / marg_chol; thread-per-IVP kernels */
+};
 enum { PN_B200_OK = 0, PN_B200_NAN = 1, PN_B200_MAX_ATTEMPTS = 2 };  /* status[b] */
 enum {
   PN_B200_FLAG_FIXED_GRID = 1, /* solve_fixed_grid (vdp.py:88-91): steps = diff(save_at), no rejection */

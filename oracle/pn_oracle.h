@@ -54,7 +54,7 @@ enum {
 enum { PN_FACT_ISOTROPIC = 0, PN_FACT_BLOCKDIAG = 1, PN_FACT_DENSE = 2 };
 enum { PN_CORR_TS0 = 0, PN_CORR_TS1 = 1 };
 enum { PN_STRATEGY_FILTER = 0, PN_STRATEGY_FIXEDPOINT = 1 };
-enum { PN_CALIB_NONE = 0, PN_CALIB_DYNAMIC = 1 };
+enum { PN_CALIB_NONE = 0, PN_CALIB_DYNAMIC = 1, PN_CALIB_MLE = 2 /* solver_mle: running quasi-MLE, see pn_solver.c */ };
 enum { PN_STATUS_OK = 0, PN_STATUS_NAN = 1, PN_STATUS_MAX_ATTEMPTS = 2 };
 
 /* Mirrors the solver construction of src/odecheckpts/ivpsolvers.py:14-53. */

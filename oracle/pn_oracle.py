@@ -26,7 +26,7 @@ PROBLEMS = {
 FACTORISATIONS = {"isotropic": 0, "blockdiag": 1, "dense": 2}
 CORRECTIONS = {"ts0": 0, "ts1": 1}
 STRATEGIES = {"filter": 0, "fixedpoint": 1}
-CALIBRATIONS = {"none": 0, "dynamic": 1}
+CALIBRATIONS = {"none": 0, "dynamic": 1, "mle": 2}
 
 
 class Config(C.Structure):

@@ -90,6 +90,7 @@ typedef struct {
   double *gain;                  /* N*r */
   double *hL, *W, *Y, *Rm, *Rs;  /* r*N, N*r, ... */
   double *sig;                   /* F */
+  double zz0, invS0, mle_x2;     /* solver_mle: sum of squared residuals, 1/S of the last attempt; z^T S^-1 z / d */
   double *keep1, *keep2, *gnew;  /* N*Ctot scratch */
   double *idG, *idL, *idg;       /* identity conditional (I, 0, 0) */
 } engine;
@@ -125,6 +126,8 @@ static int engine_init(engine *E, const pn_oracle_config *cfg) {
     return -3;
   }
   if (cfg->correction == PN_CORR_TS1 && !pn_problem_has_jacobian(cfg->problem)) return -4;
+  /* solver_mle: one factor set with a scalar innovation variance (isotropic, dense with d = 1) */
+  if (cfg->calibration == PN_CALIB_MLE && (E->F != 1 || E->r != 1)) return -6;
   E->dense = (E->r > 1);
   E->blk = (E->dense && cfg->dense_block > 0) ? cfg->dense_block : 0;
   if (E->blk > 64) return -5;
@@ -456,6 +459,7 @@ static void calibrate_and_estimate(engine *E, double dt) {
     for (int f = 0; f < E->F; ++f) {
       int c0 = f * E->C;
       double zz = sum_squares(E, E->z + c0, E->C);
+      if (f == 0) E->zz0 = zz;
       double sigma_hat = (sqrt(zz) * (1.0 / s)) * E->inv_sqrt_C;
       E->sig[f] = sigma_hat;
       double er = (adt * sigma_hat) * s;
@@ -501,6 +505,7 @@ static void correct_cov_one(engine *E, const double *L_ext, double *L_new) {
       S = fma(acc, acc, S);
     }
     double invS = 1.0 / S;
+    E->invS0 = invS;
     for (int i = 0; i < N; ++i) {
       double acc = 0.0;
       for (int j = 0; j < N; ++j) acc = fma(L_ext[i * N + j], hL[j], acc);
@@ -612,6 +617,9 @@ static void attempt_step(engine *E, const double *params, const pstate *S, doubl
     correct_mean_one(E, P->mean, f * E->C, E->C);
   }
   P->t = S->t + dt;
+  /* solver_mle (probdiffeq's running-mean calibration, no call site in the reference, [P?]): the whitened
+   * squared residual of this step under the innovation covariance S, per ODE dimension */
+  E->mle_x2 = (E->zz0 * E->invS0) * (1.0 / (double)E->C);
   /* scaled error norm: uses the PROPOSED u only (App. A.3, quirk confirmed against the golden) */
   for (int l = 0; l < d; ++l) E->fbuf[l] = E->err[l] * (1.0 / fma(rtol, fabs(P->mean[l]), atol));
   double acc = sum_squares(E, E->fbuf, d);
@@ -688,6 +696,7 @@ static int has_nan(const double *x, size_t k) {
 typedef struct {
   pstate step_from, interp_from, proposed;
   double dt, e_prev;
+  double mle_ss; /* solver_mle: sum of mle_x2 over the accepted steps */
   int64_t n_accepted, n_rejected, n_attempts;
 } adaptive_state;
 
@@ -710,6 +719,7 @@ static int adaptive_step(engine *E, const double *params, adaptive_state *A, dou
       A->step_from = A->proposed;
       A->proposed = tmp;
       A->n_accepted += 1;
+      A->mle_ss = A->mle_ss + E->mle_x2;
       return PN_STATUS_OK;
     }
     A->n_rejected += 1;
@@ -721,6 +731,7 @@ static void adaptive_alloc(engine *E, adaptive_state *A) {
   pstate_alloc(E, &A->interp_from);
   pstate_alloc(E, &A->proposed);
   A->n_accepted = A->n_rejected = A->n_attempts = 0;
+  A->mle_ss = 0.0;
 }
 static void adaptive_free(adaptive_state *A) {
   pstate_free(&A->step_from);
@@ -902,6 +913,9 @@ static int solve_save_at_impl(engine *E, const double *u0, const double *params,
       pstate_copy(E, &A.interp_from, &A.step_from);
     }
     if (n_accepted) n_accepted[k] = A.n_accepted;
+    if (E->cfg.calibration == PN_CALIB_MLE) /* solution.output_scale: the running MLE at emission */
+      for (int f = 0; f < E->F; ++f)
+        emit[k].sigma[f] = output_scale0 * ((A.n_accepted > 0) ? sqrt(A.mle_ss * (1.0 / (double)A.n_accepted)) : 1.0);
     k_done = k;
   }
   if (st == PN_STATUS_OK && has_nan(emit[K - 1].mean, NC)) st = PN_STATUS_NAN;
@@ -915,11 +929,16 @@ static int solve_save_at_impl(engine *E, const double *u0, const double *params,
     pstate_alloc(E, &rv);
     pstate_alloc(E, &rv_prev);
     pstate_copy(E, &rv, &emit[K - 1]);
+    /* solver_mle: the final quasi-MLE rescales the posterior covariances */
+    double mle_sc = 1.0;
+    if (E->cfg.calibration == PN_CALIB_MLE && A.n_accepted > 0) mle_sc = sqrt(A.mle_ss * (1.0 / (double)A.n_accepted));
     for (int64_t k = K - 1; k >= 0; --k) {
       for (int l = 0; l < d; ++l) u[k * d + l] = rv.mean[l];
       marginal_std(E, rv.chol, u_std + k * d);
+      for (int l = 0; l < d; ++l) u_std[k * d + l] = mle_sc * u_std[k * d + l];
       if (marg_mean) memcpy(marg_mean + (size_t)k * NC, rv.mean, sizeof(double) * NC);
-      if (marg_chol) memcpy(marg_chol + (size_t)k * FNN, rv.chol, sizeof(double) * FNN);
+      if (marg_chol)
+        for (size_t e = 0; e < FNN; ++e) marg_chol[(size_t)k * FNN + e] = mle_sc * rv.chol[e];
       if (k == 0) break;
       if (fixedpoint) {
         marginalise(E, &rv, &emit[k], &rv_prev);

@@ -85,7 +85,7 @@ for fact in ("blockdiag", "isotropic"):
 
 # C5: Brusselator ensemble over the diffusion parameter
 rng = np.random.default_rng(3)
-for N, B in ((16, 1024), (128, 296), (512, 148)):
+for N, B in ((16, 1024), (128, 296), (128, 1184), (512, 148)):
     alpha = (1.0 / 50.0) * 10.0 ** rng.uniform(-0.5, 0.5, B)
     y0 = np.concatenate([np.sin(2 * np.pi * np.linspace(0, 1, N)) + 1, 3 * np.ones(N)])
     if N == 512 and "--big" not in sys.argv:

@@ -76,3 +76,39 @@ def test_reported_standard_deviations_are_calibrated(cabi):
             assert 1e-3 < np.median(ratio) < 10.0, (fact, tol, np.median(ratio))
             assert ratio.max() < 100.0, (fact, tol, ratio.max())
             assert err.max() < 300 * tol
+
+
+@pytest.mark.parametrize("problem,d,nu,q,P,params,u0,fact,corr,t1", [
+    ("van_der_pol", 1, 4, 2, 1, (5.0,), np.array([[2.0], [0.0]]), "dense", "ts1", 3.0),
+    ("logistic", 1, 3, 1, 2, (1.0, 1.0), np.array([[0.1]]), "isotropic", "ts0", 2.5),
+    ("rigid_body", 3, 4, 1, 3, (-2.0, 1.25, -0.5), np.array([[1.0, 0.0, 0.9]]), "isotropic", "ts0", 10.0),
+])  # fmt: skip
+def test_solver_mle_matches_the_oracle_and_rescales_the_uncalibrated_posterior(cabi, problem, d, nu, q, P, params, u0, fact, corr, t1):
+    """ivpsolvers.solver_mle (no call site in the reference, restated from probdiffeq): the solve runs
+    with the initial output scale, the running quasi-MLE is reported per checkpoint and its final value scales the
+    posterior standard deviations.  GPU vs oracle bit for bit; means equal the uncalibrated solver's."""
+    from oracle import pn_oracle
+
+    K, tol, B = 9, 1e-5, 3
+    save_at = np.linspace(0.0, t1, K)
+    rng = np.random.default_rng(1)
+    u0b = u0[None] * (1.0 + 0.01 * rng.standard_normal((B, 1, 1)))
+    par = np.tile(params, (B, 1))
+    mk = lambda calib: cabi.Desc(cabi.PROBLEM_IDS[problem], d, nu, q, cabi.FACTORISATIONS[fact], cabi.CORRECTIONS[corr], 1,  # noqa: E731
+                                 cabi.CALIBRATIONS[calib], tol, tol, 0.01, 0.95, 0.2, 10.0, 0.3, 0.4, B, K, 0, P, 0, 0)
+    mle = cabi.solve_host(mk("mle"), u0b, par, None, save_at, None, full=True)
+    none = cabi.solve_host(mk("none"), u0b, par, None, save_at, None, full=True)
+    assert (mle["status"] == 0).all()
+    np.testing.assert_array_equal(mle["u"], none["u"])
+    np.testing.assert_array_equal(mle["n_accepted"], none["n_accepted"])
+    scale = mle["output_scale"][:, -1]
+    assert (scale > 0).all() and np.isfinite(scale).all()
+    np.testing.assert_array_equal(mle["u_std"], scale[:, None, None] * none["u_std"])
+    cfg = pn_oracle.make_config(problem, d, nu, q, factorisation=fact, correction=corr, calibration="mle", atol=tol, rtol=tol,
+                                dt0=0.01, num_params=P)  # fmt: skip
+    for b in range(B):
+        ora = pn_oracle.solve_save_at_lml(cfg, u0b[b], par[b], save_at, np.zeros((K, d)), np.ones(K))
+        np.testing.assert_array_equal(mle["u"][b], ora["u"])
+        np.testing.assert_array_equal(mle["u_std"][b], ora["u_std"])
+        np.testing.assert_array_equal(mle["output_scale"][b, 1:], ora["output_scale"][1:, 0])
+        np.testing.assert_array_equal(mle["marg_chol"][b].reshape(K, -1), ora["marg_chol"].reshape(K, -1))

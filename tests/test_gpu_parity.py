@@ -411,6 +411,31 @@ def test_wide_brusselator_ensemble_beyond_one_member_per_sm(cabi, oracle):
     _assert_bitwise({k: v[idx] for k, v in many.items()}, ora)
 
 
+def test_wide_brusselator_one_warp_per_ivp_build_for_large_ensembles(cabi, oracle, monkeypatch):
+    # from four members per SM on (592) the CTA-per-IVP family runs one WARP per IVP (the factor arithmetic every
+    # thread replicates is then issued once, eight members fit an SM): same algorithm, norms summed by a 32-lane
+    # butterfly (oracle reduction_group = 32)
+    N, B, K = 24, 700, 5
+    rng = np.random.default_rng(6)
+    alpha = (1.0 / 50.0) * 10.0 ** rng.uniform(-0.5, 0.5, B)
+    u0 = np.tile(pu.brusselator_u0(N)[None], (B, 1, 1))
+    save_at = np.linspace(0.0, 1.0, K)
+    kw = dict(atol=1e-6, rtol=1e-6, dt0=0.01, P=1)
+    desc = _desc(cabi, "brusselator", 2 * N, 4, 1, B, K, **kw)
+    assert cabi.kernel_info(desc)["threads_per_cta"] == 32
+    got = cabi.solve_host(desc, u0, alpha[:, None], None, save_at, None)
+    assert (got["status"] == 0).all()
+    idx = [0, 1, 350, 699]
+    ora = oracle.solve_save_at_batch(_ocfg(oracle, "brusselator", 2 * N, 4, 1, reduction_group=32, **kw), u0[idx], alpha[idx, None], save_at)
+    _assert_bitwise({k: v[idx] for k, v in got.items()}, ora)
+    # forcing it for a small ensemble gives the same numbers as the 128-thread build to rounding (different norm order)
+    monkeypatch.setenv("PN_B200_WIDE_WARP", "1")
+    small = cabi.solve_host(_desc(cabi, "brusselator", 2 * N, 4, 1, 4, K, **kw), u0[:4], alpha[:4, None], None, save_at, None)
+    monkeypatch.setenv("PN_B200_WIDE_WARP", "0")
+    ref = cabi.solve_host(_desc(cabi, "brusselator", 2 * N, 4, 1, 4, K, **kw), u0[:4], alpha[:4, None], None, save_at, None)
+    np.testing.assert_allclose(small["u"], ref["u"], rtol=1e-9, atol=1e-12)
+
+
 def test_wide_kernel_shared_memory_sizes_in_any_order(cabi):
     # one kernel, launched with different dynamic shared-memory sizes (2 d staging doubles + mean arrays):
     # large -> small -> large must work (the function attribute is only ever raised)

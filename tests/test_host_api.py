@@ -124,8 +124,15 @@ def test_builder_vocabulary_and_descriptor_assembly():
     d = ivpsolve._make_desc(field, nu, fact, solver, 1e-3, 1e-3, ctrl, 0.01, 1, 2)
     assert (d.problem, d.nu, d.ode_order, d.factorisation, d.correction, d.strategy, d.calibration) == (5, 4, 2, 2, 1, 0, 1)
     assert _cabi.supported(d)
-    with pytest.raises(NotImplementedError):
-        ivpsolvers.strategy_smoother(ibm, ts1)
+    # the textbook smoother is a strategy of the builder vocabulary; it has no descriptor of its own (it is served
+    # by solve_adaptive_save_every_step + stats.offgrid_marginals_searchsorted over the fixed-point kernel)
+    smoother = ivpsolvers.solver_dynamic(ivpsolvers.strategy_smoother(ibm, ts1))
+    assert smoother.strategy.name == "smoother"
+    with pytest.raises(ValueError):
+        ivpsolve._make_desc(field, nu, fact, smoother, 1e-3, 1e-3, ctrl, 0.01, 1, 2)
+    mle = ivpsolvers.solver_mle(ivpsolvers.strategy_fixedpoint(ibm, ts1))
+    d_mle = ivpsolve._make_desc(field, nu, fact, mle, 1e-3, 1e-3, ctrl, 0.01, 1, 2)
+    assert d_mle.calibration == 2 and _cabi.supported(d_mle)
     with pytest.raises(ValueError):
         ivpsolve._make_desc(field, 3, fact, solver, 1e-3, 1e-3, ctrl, 0.01, 1, 2)
 

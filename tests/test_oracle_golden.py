@@ -142,3 +142,23 @@ def test_smoothed_initial_value_reproduces_u0(oracle):
     cfg = oracle.make_config("brusselator", 8, 4, 1, atol=1e-8, rtol=1e-8, dt0=0.01, num_params=1)
     out = oracle.solve_save_at(cfg, pu.brusselator_u0(4), [0.02], np.linspace(0.0, 10.0, 200))
     np.testing.assert_allclose(out["u"][0], pu.brusselator_u0(4)[0], rtol=0, atol=5e-15)
+
+
+def test_solver_mle_is_the_uncalibrated_solve_with_rescaled_covariances(oracle):
+    """solver_mle restated (no call site in the reference): same means and steps as the uncalibrated
+    solver; standard deviations multiplied by the final running quasi-MLE; the MLE equals the RMS of the per-step
+    whitened residuals, which for dynamic calibration would be the per-step scales themselves."""
+    import numpy as np
+
+    save_at = np.linspace(0.0, 2.5, 6)
+    kw = dict(atol=1e-5, rtol=1e-5, dt0=0.1, num_params=2)
+    a = oracle.solve_save_at_lml(oracle.make_config("logistic", 1, 3, 1, calibration="mle", **kw), [[0.1]], [1.0, 1.0], save_at,
+                                 np.zeros((6, 1)), np.ones(6))  # fmt: skip
+    b = oracle.solve_save_at_lml(oracle.make_config("logistic", 1, 3, 1, calibration="none", **kw), [[0.1]], [1.0, 1.0], save_at,
+                                 np.zeros((6, 1)), np.ones(6))  # fmt: skip
+    np.testing.assert_array_equal(a["u"], b["u"])
+    s = a["output_scale"][-1, 0]
+    assert 0 < s < 10
+    np.testing.assert_allclose(a["u_std"], s * b["u_std"], rtol=1e-15)
+    # the running value moves from checkpoint to checkpoint and ends at the final scale
+    assert len(set(np.round(a["output_scale"][1:, 0], 12))) > 1
