@@ -50,6 +50,13 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_rows_kernel(const __grid_
   constexpr int GPW = 32 / LANES;  // IVPs per warp
   static_assert(LANES == 16 || LANES == 32, "LANES must be 16 or 32");
   static_assert(Dn <= LANES, "one lane per state row");
+  // The observation matrix H = E_q - J only touches the derivatives 0 .. q, and L_Q (x) I and L_ext are lower
+  // triangular: H p (L_Q (x) I) and H L_ext are exactly zero from column LIM = (q+1) d on.  The matrices the
+  // calibration, the innovation and the corrected factor triangularise therefore have their sub-diagonal
+  // non-zeros in the first LIM rows only, and the generic QR leaves a column with an all-zero sub-diagonal
+  // untouched: the loops below stop at LIM (exact -- same bits as the full loops, 9 of 14 reflectors of the
+  // corrected factor and 60 % of every inner product of the two d-column QRs skipped at D = 15).
+  constexpr int LIM = ((Q + 1) * d < Dn) ? (Q + 1) * d : Dn;
 
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -115,34 +122,34 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_rows_kernel(const __grid_
   // l of X^T where X is d x Dn row-major in shared memory.  Publishes the d x d factor to Rs.
   auto small_qr = [&](const double* X) {
     const int lr = (c < d) ? c : (d - 1);
-    double rm[Dn];
+    double rm[LIM];
 #pragma unroll
-    for (int i = 0; i < Dn; ++i) rm[i] = X[lr * Dn + i];
+    for (int i = 0; i < LIM; ++i) rm[i] = X[lr * Dn + i];
 #pragma unroll
     for (int j = 0; j < d; ++j) {
       double* vbj = vb + (j & 1) * VB;
       if (c == j) {
 #pragma unroll
-        for (int i = j; i < Dn; ++i) vbj[i] = rm[i];
+        for (int i = j; i < LIM; ++i) vbj[i] = rm[i];
       }
       __syncwarp();
       const double alpha = vbj[j];
-      double v[Dn];
+      double v[LIM];
       double sigma2 = 0.0;
 #pragma unroll
-      for (int i = j + 1; i < Dn; ++i) {
+      for (int i = j + 1; i < LIM; ++i) {
         v[i] = vbj[i];
         sigma2 = fma(v[i], v[i], sigma2);
       }
       const Reflector R = make_reflector(alpha, sigma2);
       double w = 0.0;
 #pragma unroll
-      for (int i = j + 1; i < Dn; ++i) w = fma(v[i], rm[i], w);
+      for (int i = j + 1; i < LIM; ++i) w = fma(v[i], rm[i], w);
       w = fma(R.v0, rm[j], w);
       const double f = w * R.g;
       const double nj = fma(-f, R.v0, rm[j]);
 #pragma unroll
-      for (int i = j + 1; i < Dn; ++i) rm[i] = fma(-f, v[i], rm[i]);
+      for (int i = j + 1; i < LIM; ++i) rm[i] = fma(-f, v[i], rm[i]);
       rm[j] = (c == j) ? R.beta : nj;
     }
     if (c < d) {
@@ -518,7 +525,7 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_rows_kernel(const __grid_
         for (int l = 0; l < d; ++l) {
           double acc = 0.0;
 #pragma unroll
-          for (int j = 0; j < Dn; ++j) acc = fma(le[j], HLs[l * Dn + j], acc);
+          for (int j = 0; j < LIM; ++j) acc = fma(le[j], HLs[l * Dn + j], acc);
           wt[l] = acc;
         }
 #pragma unroll
@@ -538,39 +545,41 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_rows_kernel(const __grid_
           gt[i] = acc * inv;
         }
       }
-      double mc[Dn];  // column cr of (L_ext - gain HL)^T
+      double mc[Dn];  // column cr of (L_ext - gain HL)^T; rows >= LIM are those of L_ext^T and never change
 #pragma unroll
       for (int j = 0; j < Dn; ++j) {
         double acc = le[j];
+        if (j < LIM) {
 #pragma unroll
-        for (int l = 0; l < d; ++l) acc = fma(-HLs[l * Dn + j], gt[l], acc);
+          for (int l = 0; l < d; ++l) acc = fma(-HLs[l * Dn + j], gt[l], acc);
+        }
         mc[j] = acc;
       }
 #pragma unroll
-      for (int j = 0; j < Dn - 1; ++j) {
+      for (int j = 0; j < LIM - 1; ++j) {
         double* vbj = vb + (j & 1) * VB;
         if (c == j) {
 #pragma unroll
-          for (int i = j; i < Dn; ++i) vbj[i] = mc[i];
+          for (int i = j; i < LIM; ++i) vbj[i] = mc[i];
         }
         __syncwarp();
         const double alpha = vbj[j];
-        double v[Dn];
+        double v[LIM];
         double sigma2 = 0.0;
 #pragma unroll
-        for (int i = j + 1; i < Dn; ++i) {
+        for (int i = j + 1; i < LIM; ++i) {
           v[i] = vbj[i];
           sigma2 = fma(v[i], v[i], sigma2);
         }
         const Reflector R = make_reflector(alpha, sigma2);
         double w = 0.0;
 #pragma unroll
-        for (int i = j + 1; i < Dn; ++i) w = fma(v[i], mc[i], w);
+        for (int i = j + 1; i < LIM; ++i) w = fma(v[i], mc[i], w);
         w = fma(R.v0, mc[j], w);
         const double f = w * R.g;
         const double nj = fma(-f, R.v0, mc[j]);
 #pragma unroll
-        for (int i = j + 1; i < Dn; ++i) mc[i] = fma(-f, v[i], mc[i]);
+        for (int i = j + 1; i < LIM; ++i) mc[i] = fma(-f, v[i], mc[i]);
         mc[j] = (c == j) ? R.beta : nj;
       }
       if (act && mode == MODE_STEP) {
