@@ -341,17 +341,15 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_rows_kernel(const __grid_
     // predict covariance: columns of [sigma LQ^T (x) I | 0 ; (A L_p)^T | L_p^T]
     {
       double lb[Dn], rb[Dn];  // bottom halves of the lane's left / right column
+      // (A L_p)[cr][k] = sum_j A1[ci][j] pinv_j L[j d + cl][k]: A1[ci][j] = 0 for j < ci, so those terms only add
+      // exact zeros in front of the first product (fma(a, x, +-0) = a x rounded): no lane-dependent selects
 #pragma unroll
       for (int k = 0; k < Dn; ++k) {
-        double acc = 0.0;
+        double acc = a1row[0] * (pinvn[0] * S_L[cl * Dn + k]);
 #pragma unroll
-        for (int j = 0; j < N; ++j) {
-          const double x = pinvn[j] * S_L[(j * d + cl) * Dn + k];
-          const double nx = fma(a1row[j], x, acc);
-          acc = (j == ci) ? (a1row[j] * x) : ((j > ci) ? nx : acc);
-          if (FIX) rb[k] = (j == ci) ? x : ((j == 0) ? 0.0 : rb[k]);
-        }
+        for (int j = 1; j < N; ++j) acc = fma(a1row[j], pinvn[j] * S_L[(j * d + cl) * Dn + k], acc);
         lb[k] = acc;
+        if (FIX) rb[k] = pic * S_L[cr * Dn + k];
       }
       for (int j = 0; j < Dn; ++j) {
         const int jq = j / d, jr = j - jq * d;
@@ -511,7 +509,7 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_rows_kernel(const __grid_
       for (int l = 0; l < d; ++l) {
         double acc = H[l * Dn] * L_ext[cr];
 #pragma unroll
-        for (int i = 1; i < Dn; ++i) acc = fma(H[l * Dn + i], L_ext[i * Dn + cr], acc);
+        for (int i = 1; i < LIM; ++i) acc = fma(H[l * Dn + i], L_ext[i * Dn + cr], acc);  // H is zero from column LIM on
         if (act) HLs[l * Dn + c] = acc;
       }
       __syncwarp();
