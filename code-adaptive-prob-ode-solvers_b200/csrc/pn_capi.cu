@@ -592,7 +592,7 @@ int pn_b200_markov_sample(const pn_b200_desc* desc, const void* workspace, size_
   int rc = make_plan(desc, &p, false);
   if (rc) return rc;
   if (desc->strategy != PN_B200_FIXEDPOINT || !p.k->launch_sample)
-    return fail(PN_B200_ERR_UNSUPPORTED, "posterior sampling needs a fixed-point solve of the thread-per-IVP or lane-per-dimension family");
+    return fail(PN_B200_ERR_UNSUPPORTED, "posterior sampling needs a fixed-point solve");
   if (!workspace || workspace_bytes < p.ws_ticket + p.ws_cond || !samples || !status || num_samples < 1)
     return fail(PN_B200_ERR_ARGUMENT, "bad sampling arguments");
   if (desc->batch == 0) return PN_B200_SUCCESS;
@@ -601,6 +601,7 @@ int pn_b200_markov_sample(const pn_b200_desc* desc, const void* workspace, size_
   a.K = desc->num_save_at;
   a.S = num_samples;
   a.dv = p.k->dv;
+  a.d = desc->d;
   a.seed = seed;
   a.cond = (const double*)((const char*)workspace + p.ws_ticket);
   a.status = status;
@@ -617,7 +618,7 @@ int pn_b200_log_marginal_likelihood(const pn_b200_desc* desc, const void* worksp
   int rc = make_plan(desc, &p, false);
   if (rc) return rc;
   if (desc->strategy != PN_B200_FIXEDPOINT || !p.k->launch_lml)
-    return fail(PN_B200_ERR_UNSUPPORTED, "the log marginal likelihood needs a fixed-point solve of the thread-per-IVP or lane-per-dimension family");
+    return fail(PN_B200_ERR_UNSUPPORTED, "the log marginal likelihood needs a fixed-point solve of the thread-per-IVP, lane-per-dimension or CTA-per-IVP isotropic family");
   if (!workspace || workspace_bytes < p.ws_ticket + p.ws_cond || !status || !data || !obs_std || !lml)
     return fail(PN_B200_ERR_ARGUMENT, "bad likelihood arguments");
   if (desc->batch == 0) return PN_B200_SUCCESS;
@@ -625,8 +626,10 @@ int pn_b200_log_marginal_likelihood(const pn_b200_desc* desc, const void* worksp
   LmlArgs a;
   a.B = desc->batch;
   a.K = desc->num_save_at;
-  a.dv = p.k->dv;
-  a.D = desc->d / p.k->dv;
+  // CTA-per-IVP isotropic family: one virtual member per column, as in the lane-per-dimension isotropic kernels
+  const int lml_dv = (p.k->family == FAMILY_WIDE) ? desc->d : p.k->dv;
+  a.dv = lml_dv;
+  a.D = desc->d / lml_dv;
   a.per_dim = (p.k->family == FAMILY_GROUP_BDIAG) ? 1 : 0;
   a.cond = (const double*)((const char*)workspace + p.ws_ticket);
   a.status = status;
@@ -634,7 +637,7 @@ int pn_b200_log_marginal_likelihood(const pn_b200_desc* desc, const void* worksp
   a.obs_std = obs_std;
   a.lml = lml;
   // scratch: whitened residuals [B][K][d] + log|s| [B*dv][K], stream-ordered
-  const size_t nw = (size_t)desc->batch * desc->num_save_at * desc->d, nl = (size_t)desc->batch * p.k->dv * desc->num_save_at;
+  const size_t nw = (size_t)desc->batch * desc->num_save_at * desc->d, nl = (size_t)desc->batch * lml_dv * desc->num_save_at;
   double* scratch = nullptr;
   cudaError_t ce = cudaMallocAsync((void**)&scratch, (nw + nl) * sizeof(double), stream);
   if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, std::string("cudaMallocAsync: ") + cudaGetErrorString(ce));

@@ -133,3 +133,113 @@ __global__ void __launch_bounds__(128) pn_lml_reduce_kernel(const LmlArgs a) {
 }
 
 }  // namespace pn
+
+namespace pn {
+
+// ---- CTA-per-IVP isotropic family: one thread per (member, column) ------------------------------------------------
+// Same backward Kalman filter; the n x n factor recursion is shared by the d columns of a member (every thread
+// replicates it, as the solver kernel does) and each thread carries its own mean column.  Scratch layout and the
+// reduction are those of the lane-per-dimension isotropic kernels (dv = d virtual members with one column each),
+// so pn_lml_reduce_kernel adds the terms in the oracle's order.
+struct WideLmlArgs {
+  long long B, K;
+  int d;
+  const double* cond;     // [B][K][wslot]
+  const double* data;     // [B][K][d]
+  const double* obs_std;  // [B][K]
+  double* w;     // [B*d][K]
+  double* logs;  // [B*d][K] (column 0 of every member is the one that is read)
+};
+
+template <int N>
+__global__ void __launch_bounds__(128) pn_wide_lml_sweep_kernel(const WideLmlArgs a) {
+  using Lay = Layout<N, 1>;
+  constexpr int WSLOT = Lay::BW + Lay::NT, M1 = N + 1;
+  const long long vb = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (vb >= a.B * a.d) return;
+  const long long b = vb / a.d;
+  const int c = (int)(vb - b * a.d);
+  const long long wslot = (long long)WSLOT + 2LL * N * a.d;
+  const double* base = a.cond + (size_t)b * a.K * wslot;
+  double m[N], L[N][N], mdummy[N][1];
+#pragma unroll
+  for (int i = 0; i < N; ++i) mdummy[i][0] = 0.0;
+  auto mean_through = [&](const double* slot) {  // m <- G m + g[:, c]
+    double mo[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      double acc = slot[WSLOT + (size_t)i * a.d + c];
+#pragma unroll
+      for (int k = 0; k < N; ++k) acc = fma(slot[i * N + k], m[k], acc);
+      mo[i] = acc;
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) m[i] = mo[i];
+  };
+  {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      m[i] = base[WSLOT + (size_t)N * a.d + (size_t)i * a.d + c];
+#pragma unroll
+      for (int j = 0; j < N; ++j) L[i][j] = (j <= i) ? base[Lay::BW + Lay::tri(i, j)] : 0.0;
+    }
+    mean_through(base);
+    marginalise_from_global<N, 1>(mdummy, L, base, 1);
+  }
+  for (long long k = a.K - 1; k >= 0; --k) {
+    double M[M1][M1];
+#pragma unroll
+    for (int i = 0; i < M1; ++i)
+#pragma unroll
+      for (int j = 0; j < M1; ++j) M[i][j] = 0.0;
+    M[0][0] = a.obs_std[b * a.K + k];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      M[1 + i][0] = (i == 0) ? L[0][0] : 0.0;
+#pragma unroll
+      for (int j = i; j < N; ++j) M[1 + i][1 + j] = L[j][i];
+    }
+#pragma unroll
+    for (int j = 0; j < M1; ++j) {
+      double sigma2 = 0.0;
+#pragma unroll
+      for (int i = j + 1; i < M1; ++i) sigma2 = fma(M[i][j], M[i][j], sigma2);
+      const Reflector rf = make_reflector(M[j][j], sigma2);
+#pragma unroll
+      for (int cc = j + 1; cc < M1; ++cc) {
+        double w = 0.0;
+#pragma unroll
+        for (int i = j + 1; i < M1; ++i) w = fma(M[i][j], M[i][cc], w);
+        w = fma(rf.v0, M[j][cc], w);
+        const double f = w * rf.g;
+        M[j][cc] = fma(-f, rf.v0, M[j][cc]);
+#pragma unroll
+        for (int i = j + 1; i < M1; ++i) M[i][cc] = fma(-f, M[i][j], M[i][cc]);
+      }
+      M[j][j] = rf.beta;
+#pragma unroll
+      for (int i = j + 1; i < M1; ++i) M[i][j] = 0.0;
+    }
+    const double sv = M[0][0], inv_s = rcp(sv);
+    a.logs[vb * a.K + k] = det_log(fabs(sv));
+    {
+      const double z = m[0] - a.data[(b * a.K + k) * a.d + c];
+      a.w[vb * a.K + k] = z * inv_s;
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        const double gi = M[0][1 + i] * inv_s;
+        m[i] = fma(-gi, z, m[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int j = 0; j < N; ++j) L[i][j] = (j <= i) ? M[1 + j][1 + i] : 0.0;
+    if (k == 0) break;
+    const double* slot = base + (size_t)k * wslot;
+    mean_through(slot);
+    marginalise_from_global<N, 1>(mdummy, L, slot, 1);
+  }
+}
+
+}  // namespace pn

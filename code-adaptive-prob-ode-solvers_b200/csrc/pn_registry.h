@@ -105,6 +105,23 @@ struct ScalarInstance {
   }
 };
 
+// posterior sampling for the dense families (row-major or transposed slots): one warp per (member, sample)
+inline cudaError_t launch_dense_sample(const SampleArgs& a, int Dn, int transposed, cudaStream_t s) {
+  constexpr int WARPS = 4;
+  DenseSampleArgs w;
+  w.B = a.B; w.K = a.K; w.S = a.S; w.Dn = Dn; w.d = a.d; w.transposed = transposed; w.seed = a.seed;
+  w.cond = a.cond; w.status = a.status; w.samples = a.samples;
+  const size_t smem = (size_t)WARPS * 3 * Dn * sizeof(double);
+  auto kern = pn_dense_sample_kernel<WARPS>;
+  if (smem > 48 * 1024) {
+    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ce != cudaSuccess) return ce;
+  }
+  const long long warps = a.B * a.S;
+  kern<<<(unsigned)((warps + WARPS - 1) / WARPS), 32 * WARPS, smem, s>>>(w);
+  return cudaGetLastError();
+}
+
 // dense factorisation with d > 1: warp per IVP
 template <class Prob, int NU, int STRAT, int WARPS>
 struct DenseInstance {
@@ -122,9 +139,12 @@ struct DenseInstance {
     kern<<<grid, 32 * WARPS, smem, s>>>(a);
     return cudaGetLastError();
   }
+  static cudaError_t launch_sample(const SampleArgs& a, cudaStream_t s) {
+    return launch_dense_sample(a, (NU + 1) * Prob::D, 0, s);
+  }
   static KernelEntry entry() {
     KernelEntry e;
-    e.launch_sample = nullptr;
+    e.launch_sample = (STRAT == 1) ? &launch_sample : nullptr;
     e.launch_lml = nullptr;
     e.ctx_doubles = 0;
     e.solve_func_sliced = nullptr;
@@ -185,10 +205,25 @@ struct WideInstance {
     pn_wide_smooth_kernel<NU + 1, STRAT, THREADS><<<(int)a.B, THREADS, 0, s>>>(w);
     return cudaGetLastError();
   }
+  static cudaError_t launch_sample(const SampleArgs& a, cudaStream_t s) {
+    WideSampleArgs w;
+    w.B = a.B; w.K = a.K; w.S = a.S; w.d = a.d; w.seed = a.seed; w.cond = a.cond; w.status = a.status; w.samples = a.samples;
+    const long long total = a.B * a.S * a.d;
+    pn_wide_sample_kernel<NU + 1><<<(unsigned)((total + 127) / 128), 128, 0, s>>>(w);
+    return cudaGetLastError();
+  }
+  // the caller passes dv = d, D = 1: the scratch layout and the reduction of the lane-per-dimension isotropic kernels
+  static cudaError_t launch_lml(const LmlArgs& a, cudaStream_t s) {
+    WideLmlArgs w;
+    w.B = a.B; w.K = a.K; w.d = a.dv; w.cond = a.cond; w.data = a.data; w.obs_std = a.obs_std; w.w = a.w; w.logs = a.logs;
+    pn_wide_lml_sweep_kernel<NU + 1><<<(unsigned)((a.B * a.dv + 127) / 128), 128, 0, s>>>(w);
+    pn_lml_reduce_kernel<0><<<(unsigned)((a.B + 127) / 128), 128, 0, s>>>(a);
+    return cudaGetLastError();
+  }
   static KernelEntry entry() {
     KernelEntry e;
-    e.launch_sample = nullptr;
-    e.launch_lml = nullptr;
+    e.launch_sample = (STRAT == 1) ? &launch_sample : nullptr;
+    e.launch_lml = (STRAT == 1) ? &launch_lml : nullptr;
     e.ctx_doubles = 0;
     e.solve_func_sliced = nullptr;
     e.launch_solve_sliced = nullptr;
@@ -257,9 +292,12 @@ struct DenseCtaInstance {
     kern<<<grid, cta::T, smem, s>>>(w);
     return cudaGetLastError();
   }
+  static cudaError_t launch_sample(const SampleArgs& a, cudaStream_t s) {
+    return launch_dense_sample(a, (NU + 1) * a.d, 1, s);  // kernel-native transposed slots
+  }
   static KernelEntry entry() {
     KernelEntry e;
-    e.launch_sample = nullptr;
+    e.launch_sample = (STRAT == 1) ? &launch_sample : nullptr;
     e.launch_lml = nullptr;
     e.ctx_doubles = 0;
     e.solve_func_sliced = nullptr;

@@ -146,7 +146,7 @@ int pn_b200_trim(int device);
  * `workspace` / `status` are the buffers the solve call used (the K backward conditionals are read
  * from the workspace); samples: [B][S][K][d] draws of the ODE solution at the checkpoints (DEVICE).
  * Random numbers are Philox4x32-10 + Box-Muller keyed by `seed`: same distribution as the reference,
- * not the same bits as jax.random.  Thread-per-IVP and lane-per-dimension kernel families.
+ * not the same bits as jax.random.  Every kernel family (isotropic / blockdiag / dense, any dimension).
  */
 int pn_b200_markov_sample(const pn_b200_desc* desc, const void* workspace, size_t workspace_bytes,
                           const int32_t* status, uint64_t seed, int64_t num_samples, double* samples,
@@ -160,7 +160,8 @@ int pn_b200_markov_sample(const pn_b200_desc* desc, const void* workspace, size_
  * at save_at[0..K-1]; obs_std: [B][K] observation noise standard deviations (> 0); lml: [B] (all
  * DEVICE pointers).  lml[b] is the running mean over the K data points of
  * log p(y_k | y_{k+1}, ..., y_{K-1}) -- probdiffeq's reverse Kalman-filter estimator -- i.e. the joint
- * log density divided by K; NaN for failed members.  Thread-per-IVP and lane-per-dimension families.
+ * log density divided by K; NaN for failed members.  Isotropic and blockdiag factorisations of any dimension and the
+ * dense factorisation with d == 1 (PN_B200_ERR_UNSUPPORTED for dense with d > 1).
  */
 int pn_b200_log_marginal_likelihood(const pn_b200_desc* desc, const void* workspace, size_t workspace_bytes,
                                     const int32_t* status, const double* data, const double* obs_std,
