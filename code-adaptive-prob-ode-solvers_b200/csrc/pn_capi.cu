@@ -254,8 +254,8 @@ static int resolve(const pn_b200_desc* d, const KernelEntry** out) {
     }
   }
   if (k && (d->flags & PN_B200_FLAG_RECORD) && k->family != FAMILY_SCALAR && k->family != FAMILY_COOP &&
-      k->family != FAMILY_GROUP_ISO && k->family != FAMILY_GROUP_BDIAG)
-    return fail(PN_B200_ERR_UNSUPPORTED, "trajectory recording is implemented for the thread-per-IVP and lane-per-dimension kernels");
+      k->family != FAMILY_GROUP_ISO && k->family != FAMILY_GROUP_BDIAG && k->family != FAMILY_WIDE)
+    return fail(PN_B200_ERR_UNSUPPORTED, "trajectory recording is implemented for the thread-per-IVP, lane-per-dimension and CTA-per-IVP isotropic kernels");
   if (!k) {
     char buf[256];
     snprintf(buf, sizeof buf, "no kernel compiled for problem=%d nu=%d factorisation=%d correction=%d strategy=%d d=%d",

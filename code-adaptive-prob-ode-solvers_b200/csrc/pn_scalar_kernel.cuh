@@ -595,14 +595,17 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
         mle_ss = 0.0;
         if (leader) a.n_accepted[b * a.K] = 0;
         emit_scale(0, sigma0);
-        if (!WIDE && (a.flags & FLAG_RECORD)) {
+        if (a.flags & FLAG_RECORD) {
           // trajectory layout: traj_t / traj_std [cap][B], traj_u [cap][d][B]; a lane of a lane-per-dimension
-          // kernel writes its own dimension, the leader the time and (its) standard deviation
+          // kernel writes its own dimension (a thread of the CTA-per-IVP kernel its own columns), the leader
+          // the time and (its) standard deviation
           if (leader) {
             a.traj_t[b] = t;
             a.traj_std[b] = 0.0;
           }
-          if (GROUP == 1) {
+          if constexpr (WIDE) {
+            for (int c = tid; c < wd; c += THREADS) a.traj_u[(long long)c * a.B + b] = Wm[c];
+          } else if (GROUP == 1) {
 #pragma unroll
             for (int c = 0; c < D; ++c) a.traj_u[(long long)c * a.B + b] = SM(0, c);
           } else if (real) {
@@ -1241,8 +1244,15 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
       for (int e = 0; e < Lay::MARG; ++e) dst[e] = s_state[e * THREADS + tid];
     };
     auto record = [&](double tt, const double (&mm)[N][D], const double (&LL)[N][N]) {
-      if (!WIDE && (a.flags & FLAG_RECORD) && n_acc < a.traj_cap) {
-        if (GROUP == 1) {
+      if ((a.flags & FLAG_RECORD) && n_acc < a.traj_cap) {
+        if constexpr (WIDE) {
+          // pass 3 has just moved the recorded mean into the state array (row 0 = u)
+          if (leader) {
+            a.traj_t[n_acc * a.B + b] = tt;
+            a.traj_std[n_acc * a.B + b] = dsqrt(fma(LL[0][0], LL[0][0], 0.0));
+          }
+          for (int c = tid; c < wd; c += THREADS) a.traj_u[((long long)n_acc * wd + c) * a.B + b] = Wm[c];
+        } else if (GROUP == 1) {
           a.traj_t[n_acc * VB + vb] = tt;
 #pragma unroll
           for (int c = 0; c < D; ++c) a.traj_u[(n_acc * D + c) * VB + vb] = mm[0][c];
@@ -1460,7 +1470,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
         if (st != 0)
           for (long long kk = k_next; kk < a.K; ++kk) a.n_accepted[b * a.K + kk] = n_acc;
       }
-      if (!WIDE && leader && (a.flags & FLAG_RECORD)) a.traj_len[b] = (n_acc + 1 < a.traj_cap) ? (n_acc + 1) : a.traj_cap;
+      if (leader && (a.flags & FLAG_RECORD)) a.traj_len[b] = (n_acc + 1 < a.traj_cap) ? (n_acc + 1) : a.traj_cap;
       have = false;
     }
   }

@@ -84,3 +84,48 @@ def test_wide_family_log_marginal_likelihood_bitwise_vs_oracle(oracle):
         np.testing.assert_array_equal(out["u"][b].cpu().numpy(), ora["u"])
         assert lml[b] == ora["lml"], (b, lml[b], ora["lml"])
     assert lml[0] != lml[1]
+
+
+def test_brusselator_textbook_smoother_on_the_cta_per_ivp_kernel(oracle):
+    """experiments/4_brusselator/run.py:51-117 at N = 32 (d = 64, the CTA-per-IVP isotropic kernel): the baseline
+    step count (solve_adaptive_terminal_values), the textbook smoother (strategy_smoother +
+    solve_adaptive_save_every_step: one backward conditional per accepted step) and the checkpoint solver
+    (strategy_fixedpoint + solve_adaptive_save_at) -- same posterior by two routes, the paper's comparison."""
+    from odecheckpts_b200 import ivps
+    from odecheckpts_b200.probdiffeq import impl, ivpsolve, taylor
+    from odecheckpts_b200.probdiffeq import ivpsolvers as pdi
+
+    N, tol, t1 = 32, 1e-6, 2.0
+    vf, u0, (t0, _), params = ivps.brusselator(N=N)
+    impl.impl.select("isotropic", ode_shape=(2 * N,))
+    ctrl = ivpsolve.control_proportional_integral()
+    ibm, ts0 = pdi.prior_ibm(num_derivatives=4), pdi.correction_ts0(ode_order=1)
+    f = lambda *y, t=None: vf(*y, t=t, p=params)  # noqa: E731
+    tcoeffs = taylor.odejet_unroll(lambda *y: vf(*y, t=t0, p=params), u0, num=4)
+
+    def adaptive(strategy):
+        solver = pdi.solver_dynamic(strategy)
+        return solver.initial_condition(tcoeffs, 1.0), ivpsolve.adaptive(solver, atol=tol, rtol=tol, control=ctrl)
+
+    init, fixedpoint = adaptive(pdi.strategy_fixedpoint(ibm, ts0))
+    base = ivpsolve.solve_adaptive_terminal_values(f, init, t0=t0, t1=t1, dt0=0.01, adaptive_solver=fixedpoint)
+    n_steps = int(base.num_steps)
+    assert n_steps > 100
+    init_s, smoother = adaptive(pdi.strategy_smoother(ibm, ts0))
+    text = ivpsolve.solve_adaptive_save_every_step(f, init_s, t0=t0, t1=t1, dt0=0.01, adaptive_solver=smoother)
+    grid = np.asarray(text.t)
+    assert len(grid) == n_steps + 1 and grid[0] == t0 and grid[-1] == t1 and text.u.shape == (n_steps + 1, 2 * N)
+    # the checkpoint solver on a coarse grid evaluates the same posterior with O(K) memory
+    save_at = np.linspace(t0, t1, 9)
+    ckpt = ivpsolve.solve_adaptive_save_at(f, init, save_at=save_at, dt0=0.01, adaptive_solver=fixedpoint)
+    assert int(ckpt.num_steps[-1]) == n_steps
+    union = np.union1d(grid, save_at)
+    both = ivpsolve._solve_on_checkpoints(text.posterior.context, union)
+    np.testing.assert_allclose(both.u[np.searchsorted(union, save_at)], ckpt.u, rtol=1e-9, atol=1e-12)
+    np.testing.assert_array_equal(both.u[np.searchsorted(union, grid)][1:-1].shape, text.u[1:-1].shape)
+    # bit-identical to the oracle run with the accepted grid as checkpoints
+    cfg = oracle.make_config("brusselator", 2 * N, 4, 1, atol=tol, rtol=tol, dt0=0.01, num_params=1, reduction_group=128)
+    ora = oracle.solve_save_at(cfg, np.asarray(u0[0])[None], list(params), grid)
+    assert ora["status"] == 0 and ora["n_accepted"][-1] == n_steps
+    np.testing.assert_array_equal(np.asarray(text.u), ora["u"])
+    np.testing.assert_array_equal(np.asarray(text.u_std), ora["u_std"])
