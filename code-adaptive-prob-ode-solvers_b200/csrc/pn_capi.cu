@@ -251,6 +251,13 @@ static int resolve(const pn_b200_desc* d, const KernelEntry** out) {
     if (k && want_warp) {
       const KernelEntry* k32 = find_kernel(FAMILY_WIDE, d->problem, d->nu, d->strategy, -32);
       if (k32) k = k32;
+    } else if (k && d->strategy == PN_B200_FIXEDPOINT && d->batch <= WIDE_SMEM_MAX_MEMBERS) {
+      // at most one member per SM: the build with a backward warp (PN_B200_WIDE_PIPE=0 switches it off for A/B runs)
+      const char* wp = getenv("PN_B200_WIDE_PIPE");
+      if (!(wp && wp[0] == '0')) {
+        const KernelEntry* kp = find_kernel(FAMILY_WIDE, d->problem, d->nu, d->strategy, -160);
+        if (kp) k = kp;
+      }
     }
   }
   if (k && (d->flags & PN_B200_FLAG_RECORD) && k->family != FAMILY_SCALAR && k->family != FAMILY_COOP &&
@@ -339,7 +346,7 @@ static int make_plan(const pn_b200_desc* d, Plan* p, bool need_device) {
     if (ce == cudaSuccess) ce = raise_smem_limit(dev, p->k->solve_func_sliced, p->smem);
     if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce));
     int occ = 0;
-    ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, p->k->solve_func, p->k->threads, p->smem);
+    ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, p->k->solve_func, p->k->threads + p->k->extra_threads, p->smem);
     if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, cudaGetErrorString(ce));
     if (occ < 1) return fail(PN_B200_ERR_CUDA, "kernel does not fit on an SM");
     p->ctas_per_sm = occ;
@@ -436,7 +443,7 @@ int pn_b200_get_kernel_info(const pn_b200_desc* desc, pn_b200_kernel_info* info)
   cudaFuncAttributes fa;
   cudaError_t ce = cudaFuncGetAttributes(&fa, p.k->solve_func);
   if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, cudaGetErrorString(ce));
-  info->threads_per_cta = p.k->threads;
+  info->threads_per_cta = p.k->threads + p.k->extra_threads;
   info->ctas_per_sm = p.ctas_per_sm;
   info->num_sms = p.num_sms;
   info->grid = p.grid;

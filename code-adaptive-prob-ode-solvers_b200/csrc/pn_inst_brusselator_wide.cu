@@ -7,3 +7,6 @@ PN_REGISTER_WIDE(BrusselatorWide, 4, 0);
 // step), so a 128-thread CTA issues it four times per attempted step.  For ensembles with several members per
 // SM the 32-thread build issues it once and keeps up to eight members resident per SM instead of two.
 PN_REGISTER_WIDE_T(BrusselatorWide, 4, 1, 32);
+// At most one member per SM, fixed-point strategy: 128 main threads + a backward warp that owns the running
+// conditional (pn_scalar_kernel.cuh, PIPE = 1): two fifths of the per-step dependency chain move off the critical path.
+PN_REGISTER_WIDE_PIPE(BrusselatorWide, 4, 1);

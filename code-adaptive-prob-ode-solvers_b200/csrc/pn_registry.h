@@ -31,6 +31,7 @@ struct KernelEntry {
   int slot_doubles;   // workspace doubles per (checkpoint, member)
   int smem_doubles;   // dynamic shared memory doubles per thread
   int threads;
+  int extra_threads = 0;  // threads of the CTA beyond `threads` that do not run the step (CTA-per-IVP PIPE build: the backward warp)
   int group;          // lanes per IVP (1: thread per IVP)
   int dv;             // lanes per IVP that own state (workspace entries per member)
   int ctx_doubles;    // doubles one parked member occupies (time-sliced scheduling); 0: not supported
@@ -191,11 +192,11 @@ struct DenseRowsInstance {
 };
 
 // isotropic problems with a large runtime dimension: CTA per IVP
-template <class Prob, int NU, int STRAT, int THREADS>
+template <class Prob, int NU, int STRAT, int THREADS, int PIPE = 0>
 struct WideInstance {
   using Lay = Layout<NU + 1, 1>;
   static cudaError_t launch_solve(const SolveArgs& a, int grid, size_t smem, cudaStream_t s) {
-    pn_scalar_kernel<Prob, NU, STRAT, 1, 0, THREADS, 1><<<grid, THREADS, smem, s>>>(a);
+    pn_scalar_kernel<Prob, NU, STRAT, 1, 0, THREADS, 1, 0, PIPE><<<grid, THREADS + 32 * PIPE, smem, s>>>(a);
     return cudaGetLastError();
   }
   static cudaError_t launch_smooth(const SmoothArgs& a, cudaStream_t s) {
@@ -234,14 +235,16 @@ struct WideInstance {
     e.nu = NU;
     e.strategy = STRAT;
     e.N = NU + 1;
-    e.D = (THREADS == 128) ? 0 : -THREADS;  // runtime dimension; -32: the one-warp-per-IVP build for large ensembles
+    // runtime dimension; -32: the one-warp-per-IVP build for large ensembles; -160: the build with a backward warp (PIPE)
+    e.D = PIPE ? -(THREADS + 32) : ((THREADS == 128) ? 0 : -THREADS);
+    e.extra_threads = 32 * PIPE;
     e.Q = Prob::Q;
     e.P = Prob::P;
     e.slot_doubles = Lay::BW + Lay::NT;  // factor part of a slot; + 2 n d per slot and 3 n d per member at run time
     e.smem_doubles = ((STRAT == 1) ? Lay::BW : 0) + Lay::PEND + Lay::MARG;  // per thread; + 2 d + warps per CTA
     e.threads = THREADS;
     e.has_jac = false;
-    e.solve_func = (const void*)&pn_scalar_kernel<Prob, NU, STRAT, 1, 0, THREADS, 1>;
+    e.solve_func = (const void*)&pn_scalar_kernel<Prob, NU, STRAT, 1, 0, THREADS, 1, 0, PIPE>;
     e.launch_solve = &launch_solve;
     e.launch_smooth = &launch_smooth;
     return e;
@@ -344,6 +347,8 @@ struct Registrar {
   static ::pn::Registrar PN_CAT(pn_reg_, __COUNTER__)(::pn::DenseCtaInstance<::pn::cta::Prob, NU, STRAT, NB, MINB>::entry())
 #define PN_REGISTER_WIDE(Prob, NU, STRAT) \
   static ::pn::Registrar PN_CAT(pn_reg_, __COUNTER__)(::pn::WideInstance<::pn::Prob, NU, STRAT, 128>::entry())
+#define PN_REGISTER_WIDE_PIPE(Prob, NU, STRAT) \
+  static ::pn::Registrar PN_CAT(pn_reg_, __COUNTER__)(::pn::WideInstance<::pn::Prob, NU, STRAT, 128, 1>::entry())
 #define PN_REGISTER_WIDE_T(Prob, NU, STRAT, THREADS) \
   static ::pn::Registrar PN_CAT(pn_reg_, __COUNTER__)(::pn::WideInstance<::pn::Prob, NU, STRAT, THREADS>::entry())
 #define PN_REGISTER_SCALAR_T(Prob, NU, STRAT, THREADS) \

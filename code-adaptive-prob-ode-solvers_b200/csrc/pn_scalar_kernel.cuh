@@ -363,6 +363,219 @@ struct GroupVf<Brusselator<NPTS>, GROUP> {
   }
 };
 
+
+// ---- PIPE = 1 (CTA-per-IVP kernel, fixed-point strategy, at most one member per SM): a fifth warp owns the
+// running backward conditional.  The n x n factor arithmetic of one attempted step is a single dependent chain
+// (every thread of the CTA replicates it), and two fifths of that chain -- the right block of the predict QR,
+// the back substitution for the smoothing gain, the merge products and the merge QR -- are not needed by the
+// NEXT step at all.  The main warps (THREADS threads) keep the filter path: predict the mean, residual, left
+// block of the predict QR, correction, error norm, controller.  Once per iteration they publish the reflectors
+// of the predict QR; the backward warp applies them to the right block, solves for X (which the main warps need
+// for the offset g of the conditional: ready before their pass 3), merges with the running conditional while
+// the main warps are already in the next step, and carries out what the bookkeeping decided (commit / reset /
+// emit to a checkpoint slot) from a small op list.  Hand-over through shared memory + named barriers
+// (producer: bar.arrive, consumer: bar.sync).  Every quantity is computed by the same operations in the same
+// order as in the PIPE = 0 kernel: results are bit-identical.
+namespace pipe {
+constexpr int BAR_JOB = 1, BAR_X = 2, BAR_ACT = 3, BAR_MAIN = 4;
+enum : int { OP_COMMIT = 1, OP_RESET = 2, OP_STORE_MERGED = 3, OP_STORE_RUNNING = 4, OP_STORE_IDENTITY = 5 };
+constexpr int MAX_OPS = 24;
+PN_DEV void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+PN_DEV void bar_arrive(int id, int count) {
+  __threadfence_block();
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+template <int N>
+struct Mail {
+  static constexpr int NT = N * (N + 1) / 2;
+  // job: main warps -> backward warp (written before BAR_JOB)
+  double BL[N * N];        // [i][j]: row i of the bottom-left block after the QR = tail of reflector j
+  double v0[N], g[N];      // reflector scalars
+  double RY[N * N];        // R factor (upper triangle)
+  double Lp[NT];           // preconditioned state factor L_p (lower, packed): the right block starts as L_p^T
+  double p[N], pinv[N];
+  int reset, exit_;
+  // backward warp -> main warps (written before BAR_X)
+  double X[N * N];         // X = RY^{-1} R12
+  int cur;                 // which buffer of R holds the running conditional
+  double R[2][N * N + NT]; // running conditional [G | Lam packed]; the other buffer receives the merged one
+  // bookkeeping: main warps -> backward warp (written before BAR_ACT)
+  int nops;
+  int op[MAX_OPS];
+  double* dst[MAX_OPS];
+};
+template <int N>
+PN_DEV Mail<N>& mail() {
+  __shared__ Mail<N> m;
+  return m;
+}
+
+template <int N>
+__device__ __noinline__ void backward_warp(Mail<N>& M, const int nmain) {
+  using Lay = Layout<N, 1>;
+  constexpr int NT = Mail<N>::NT, OFF_LAM = N * N + N;
+  const int lane = threadIdx.x & 31, total = nmain + 32;
+  int cur = 0;
+  auto set_identity = [&](double* R) {
+    for (int e = lane; e < N * N + NT; e += 32) R[e] = (e < N * N && (e / N) == (e % N)) ? 1.0 : 0.0;
+    __syncwarp();
+  };
+  // slot factor part: [G (n x n) | n zeros | Lam (packed)]
+  auto store_factor = [&](double* dst, const double* R) {
+    for (int e = lane; e < N * N + N + NT; e += 32)
+      dst[e] = (R == nullptr) ? ((e < N * N && (e / N) == (e % N)) ? 1.0 : 0.0)
+                              : ((e < N * N) ? R[e] : ((e < OFF_LAM) ? 0.0 : R[N * N + (e - OFF_LAM)]));
+  };
+  for (;;) {
+    bar_sync(BAR_JOB, total);
+    if (M.exit_) return;
+    if (M.reset) set_identity(M.R[cur]);
+    double BL[N][N], BR[N][N], R12[N][N], RY[N][N], v0[N], gg[N], p[N], pinv[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      v0[i] = M.v0[i];
+      gg[i] = M.g[i];
+      p[i] = M.p[i];
+      pinv[i] = M.pinv[i];
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        BL[i][j] = M.BL[i * N + j];
+        RY[i][j] = (j >= i) ? M.RY[i * N + j] : 0.0;
+        BR[i][j] = (i <= j) ? M.Lp[Lay::tri(j, i)] : 0.0;  // L_p^T (upper)
+      }
+    }
+    // the reflectors of the predict QR applied to the right block [0 ; L_p^T] (pn_scalar_kernel: "right block columns")
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+#pragma unroll
+      for (int c = 0; c < N; ++c) {
+        double w = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          if (j == 0 && i > c) continue;  // still structurally zero
+          w = fma(BL[i][j], BR[i][c], w);
+        }
+        const double f = w * gg[j];
+        R12[j][c] = fma(-f, v0[j], 0.0);
+#pragma unroll
+        for (int i = 0; i < N; ++i) BR[i][c] = fma(-f, BL[i][j], BR[i][c]);
+      }
+    }
+    // X = RY^{-1} R12 (back substitution); G_p = X^T
+    double X[N][N];
+#pragma unroll
+    for (int i = N - 1; i >= 0; --i) {
+      const double inv = rcp(RY[i][i]);
+#pragma unroll
+      for (int c = 0; c < N; ++c) {
+        double acc = R12[i][c];
+#pragma unroll
+        for (int k = i + 1; k < N; ++k) acc = fma(-RY[i][k], X[k][c], acc);
+        X[i][c] = acc * inv;
+      }
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int c = 0; c < N; ++c) M.X[i * N + c] = X[i][c];
+      M.cur = cur;
+    }
+    bar_arrive(BAR_X, total);
+    // new conditional (un-preconditioned) and the merge with the running one (A.4)
+    double Gn[N][N], Ln[N][N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+#pragma unroll
+      for (int j = 0; j < N; ++j) Gn[i][j] = (p[i] * X[j][i]) * pinv[j];
+#pragma unroll
+      for (int j = 0; j < N; ++j) Ln[i][j] = p[i] * BR[j][i];
+    }
+    const double* Rc = M.R[cur];
+    double* Rn = M.R[cur ^ 1];
+    double G1[N][N], Mt[N][N], Mb[N][N];
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int j = 0; j < N; ++j) G1[i][j] = Rc[i * N + j];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        double acc = G1[i][0] * Gn[0][j];
+#pragma unroll
+        for (int k = 1; k < N; ++k) acc = fma(G1[i][k], Gn[k][j], acc);
+        if (lane == 0) Rn[i * N + j] = acc;  // merged G
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        double acc = G1[i][0] * Ln[0][j];
+#pragma unroll
+        for (int k = 1; k < N; ++k) acc = fma(G1[i][k], Ln[k][j], acc);
+        Mt[j][i] = acc;
+      }
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+      for (int i = 0; i < N; ++i) Mb[i][j] = (i <= j) ? Rc[N * N + Lay::tri(j, i)] : 0.0;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      double sigma2 = 0.0;
+#pragma unroll
+      for (int i = j + 1; i < N; ++i) sigma2 = fma(Mt[i][j], Mt[i][j], sigma2);
+#pragma unroll
+      for (int i = 0; i <= j; ++i) sigma2 = fma(Mb[i][j], Mb[i][j], sigma2);
+      const Reflector rf = make_reflector(Mt[j][j], sigma2);
+#pragma unroll
+      for (int c = j + 1; c < N; ++c) {
+        double w = 0.0;
+#pragma unroll
+        for (int i = j + 1; i < N; ++i) w = fma(Mt[i][j], Mt[i][c], w);
+#pragma unroll
+        for (int i = 0; i <= j; ++i) w = fma(Mb[i][j], Mb[i][c], w);
+        w = fma(rf.v0, Mt[j][c], w);
+        const double f = w * rf.g;
+        Mt[j][c] = fma(-f, rf.v0, Mt[j][c]);
+#pragma unroll
+        for (int i = j + 1; i < N; ++i) Mt[i][c] = fma(-f, Mt[i][j], Mt[i][c]);
+#pragma unroll
+        for (int i = 0; i <= j; ++i) Mb[i][c] = fma(-f, Mb[i][j], Mb[i][c]);
+      }
+      Mt[j][j] = rf.beta;
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) Rn[N * N + Lay::tri(i, j)] = Mt[j][i];  // merged Lam (lower)
+    }
+    __syncwarp();
+    // what the bookkeeping of this iteration decided
+    bar_sync(BAR_ACT, total);
+    const int nops = M.nops;
+    for (int o = 0; o < nops; ++o) {
+      const int op = M.op[o];
+      double* dst = M.dst[o];
+      if (op == OP_COMMIT) {
+        cur ^= 1;
+      } else if (op == OP_RESET) {
+        set_identity(M.R[cur]);
+      } else if (op == OP_STORE_MERGED) {
+        store_factor(dst, M.R[cur ^ 1]);
+      } else if (op == OP_STORE_RUNNING) {
+        store_factor(dst, M.R[cur]);
+      } else if (op == OP_STORE_IDENTITY) {
+        store_factor(dst, nullptr);
+      }
+    }
+    __syncwarp();
+  }
+}
+}  // namespace pipe
+
 #ifndef PN_MINBLOCKS
 #define PN_MINBLOCKS 2
 #endif
@@ -375,8 +588,8 @@ struct GroupVf<Brusselator<NPTS>, GROUP> {
 //           same factor arithmetic as a thread-per-IVP lane; the n x d mean arrays live in global
 //           memory (L2 resident) and each thread owns the columns c = tid, tid + THREADS, ...;
 //           norms are reduced over the CTA.  Prob::D is a dummy (1) in this mode.
-template <class Prob, int NU, int STRAT, int GROUP, int BDIAG, int THREADS, int WIDE = 0, int SLICE = 0>
-__global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const __grid_constant__ SolveArgs a) {
+template <class Prob, int NU, int STRAT, int GROUP, int BDIAG, int THREADS, int WIDE = 0, int SLICE = 0, int PIPE = 0>
+__global__ void __launch_bounds__(THREADS + 32 * PIPE, PIPE ? 1 : PN_MINBLOCKS) pn_scalar_kernel(const __grid_constant__ SolveArgs a) {
   constexpr int N = NU + 1, DT = Prob::D, D = (GROUP > 1) ? 1 : DT, Q = Prob::Q, P = (Prob::P > 0 ? Prob::P : 1);
   constexpr int DV = (GROUP > 1) ? DT : 1;  // lanes ("virtual members") per IVP that own state
   static_assert(GROUP == 1 || (GROUP >= DT && (GROUP & (GROUP - 1)) == 0 && GROUP <= 32), "bad GROUP");
@@ -385,6 +598,19 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
   constexpr bool FIX = (STRAT == 1);
   constexpr int SLOT = FIX ? Lay::SLOT_FIX : Lay::SLOT_FILT;
   constexpr double TIME_EPS = 10.0 * 2.220446049250313e-16;
+  static_assert(!PIPE || (WIDE && STRAT == 1 && GROUP == 1), "PIPE: CTA-per-IVP kernel with the fixed-point strategy");
+  if constexpr (PIPE) {
+    if (threadIdx.x >= THREADS) {  // the backward warp
+      pipe::backward_warp<N>(pipe::mail<N>(), THREADS);
+      return;
+    }
+  }
+  // barrier over the threads that run the step (PIPE: the main warps only)
+  auto cta_sync = [&]() {
+    if constexpr (PIPE) pipe::bar_sync(pipe::BAR_MAIN, THREADS); else __syncthreads();
+  };
+  bool pipe_reset = false;  // PIPE: the next job is the first of a member
+  int pipe_nops = 0;        // PIPE: ops queued for the backward warp in this iteration
 
   extern __shared__ double smem[];
   // [element][thread]
@@ -425,9 +651,9 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
     // fixed order: per-warp butterfly, then the warp sums added in warp order
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, off);
-    __syncthreads();
+    cta_sync();
     if ((tid & 31) == 0) s_red[tid >> 5] = v;
-    __syncthreads();
+    cta_sync();
     double r = s_red[0];
 #pragma unroll
     for (int w = 1; w < THREADS / 32; ++w) r = r + s_red[w];
@@ -478,9 +704,9 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
         tk = claimed_none ? (unsigned long long)a.B : (unsigned long long)c;
       } else if constexpr (WIDE) {
         __shared__ unsigned long long s_ticket;
-        __syncthreads();
+        cta_sync();
         if (tid == 0) s_ticket = atomicAdd(a.ticket, 1ULL);
-        __syncthreads();
+        cta_sync();
         tk = s_ticket;
       } else {
         if (sub == 0) tk = atomicAdd(a.ticket, 1ULL);
@@ -519,7 +745,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
             for (int i = 1; i < N; ++i) Wm[(size_t)i * wd + c] = 0.0;
             for (int i = 0; i < N; ++i) Wg[(size_t)i * wd + c] = 0.0;
           }
-          __syncthreads();
+          cta_sync();
           for (int k = 0; k < NU; ++k) {
             for (int gi = tid; gi < wN; gi += THREADS) {
               double uj[N], vj[N], u2[N];
@@ -547,7 +773,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
               Wm[(size_t)(k + 1) * wd + gi] = fu / (double)(k + 1);
               Wm[(size_t)(k + 1) * wd + wN + gi] = fv / (double)(k + 1);
             }
-            __syncthreads();
+            cta_sync();
           }
           {
             double fact = 1.0;
@@ -556,7 +782,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
               for (int c = tid; c < wd; c += THREADS) Wm[(size_t)k * wd + c] = fact * Wm[(size_t)k * wd + c];
             }
           }
-          __syncthreads();
+          cta_sync();
 #pragma unroll
           for (int i = 0; i < N; ++i) SM(i, 0) = 0.0;  // dummy register column
         } else {
@@ -591,6 +817,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
         sigma_state = sigma0;
         mode = MODE_STEP;
         k_next = 1;
+        pipe_reset = true;
         n_acc = n_rej = n_att = 0;
         mle_ss = 0.0;
         if (leader) a.n_accepted[b * a.K] = 0;
@@ -648,6 +875,10 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
     // warp-level vote keeps the loop convergent; the lane counts feed the utilisation statistics
     const unsigned active = __ballot_sync(0xffffffffu, have);
     if (active == 0u) {
+      if constexpr (PIPE) {  // (have is uniform over the CTA in this mode: every main warp leaves here)
+        if (tid == 0) pipe::mail<N>().exit_ = 1;
+        pipe::bar_arrive(pipe::BAR_JOB, THREADS + 32);
+      }
       if (!SLICE || __all_sync(0xffffffffu, exhausted)) break;
       if ((threadIdx.x & 31) == 0) slice_repair(&a, (int)((a.K - 2) >> a.slice_shift) + 1);
       __nanosleep(5000);  // members are still running elsewhere and may yet be parked
@@ -758,7 +989,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
         s_ubuf[c] = p[0] * e0;
         s_zbuf[c] = p[1] * e1;  // m_ext[q = 1][c] for now
       }
-      __syncthreads();
+      cta_sync();
       const double cc = par[0] * (double)((wN + 1) * (wN + 1));
       double acc = 0.0;
       for (int c = tid; c < wd; c += THREADS) {
@@ -834,12 +1065,13 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
       double RY[N][N];   // upper
       double R12[N][N];  // full (fixed-point)
       double BR[N][N];   // bottom-right block, starts as L_p^T (upper), fills in (fixed-point)
-      if (FIX) {
+      if (FIX && !PIPE) {
 #pragma unroll
         for (int i = 0; i < N; ++i)
 #pragma unroll
           for (int c = 0; c < N; ++c) BR[i][c] = (i <= c) ? L_p[c][i] : 0.0;
       }
+      double pipe_v0[N], pipe_g[N];  // PIPE: the reflector scalars go to the backward warp
 #pragma unroll
       for (int j = 0; j < N; ++j) {
         double sigma2 = 0.0;
@@ -848,6 +1080,10 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
         const double alpha = sigma * LQ[j * N + j];
         Reflector rf = make_reflector(alpha, sigma2);
         RY[j][j] = rf.beta;
+        if constexpr (PIPE) {
+          pipe_v0[j] = rf.v0;
+          pipe_g[j] = rf.g;
+        }
         // left block columns c > j
 #pragma unroll
         for (int c = j + 1; c < N; ++c) {
@@ -861,7 +1097,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
 #pragma unroll
           for (int i = 0; i < N; ++i) BL[i][c] = fma(-f, BL[i][j], BL[i][c]);
         }
-        if (FIX) {
+        if (FIX && !PIPE) {
           // right block columns: top entry starts at 0
 #pragma unroll
           for (int c = 0; c < N; ++c) {
@@ -882,7 +1118,30 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
       for (int i = 0; i < N; ++i)
 #pragma unroll
         for (int j = 0; j <= i; ++j) L_ext[i][j] = p[i] * RY[j][i];
-      if (FIX) {
+      if constexpr (PIPE) {
+        // hand the reflectors to the backward warp (one main warp writes: every thread holds the same values)
+        if (tid < 32) {
+          pipe::Mail<N>& M = pipe::mail<N>();
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+            M.v0[i] = pipe_v0[i];
+            M.g[i] = pipe_g[i];
+            M.p[i] = p[i];
+            M.pinv[i] = pinv[i];
+#pragma unroll
+            for (int j = 0; j < N; ++j) M.BL[i * N + j] = BL[i][j];
+#pragma unroll
+            for (int j = i; j < N; ++j) M.RY[i * N + j] = RY[i][j];
+#pragma unroll
+            for (int j = 0; j <= i; ++j) M.Lp[Lay::tri(i, j)] = L_p[i][j];
+          }
+          M.reset = pipe_reset ? 1 : 0;
+          M.exit_ = 0;
+        }
+        pipe_reset = false;
+        pipe::bar_arrive(pipe::BAR_JOB, THREADS + 32);
+      }
+      if (FIX && !PIPE) {
         // The lower-right block BR is NOT triangularised: BR^T is already a valid square-root factor
         // of the backward noise (BR^T BR = R_XY^T R_XY) and the merge below re-triangularises anyway.
         // That removes n-1 serial Householder chains per step.
@@ -923,7 +1182,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
     // merge with the running conditional (A.4); running conditional lives in shared memory
     double Gm[N][N], gm[N][D], Lm[N][N];
     auto merge_running_conditional = [&]() {
-    if (FIX) {
+    if (FIX && !PIPE) {
       double G1[N][N];
 #pragma unroll
       for (int i = 0; i < N; ++i)
@@ -1094,6 +1353,30 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
     }
     // ==================== per-lane bookkeeping (cheap, may diverge) =====================
     // helpers -------------------------------------------------------------------------
+    // PIPE: the backward warp has published X by now (it is busy with the merge); the running G the offset
+    // update needs is the buffer it is NOT writing.  Everything the bookkeeping below wants done to the
+    // running conditional is queued as an op and handed over in one piece (BAR_ACT).
+    const double* pipe_G1 = nullptr;
+    if constexpr (PIPE) {
+      pipe::bar_sync(pipe::BAR_X, THREADS + 32);
+      const pipe::Mail<N>& M = pipe::mail<N>();
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int c = 0; c < N; ++c) X[i][c] = M.X[i * N + c];
+      pipe_G1 = M.R[M.cur];
+      pipe_nops = 0;
+    }
+    auto pipe_op = [&](int code, double* dst) {
+      if constexpr (PIPE) {
+        if (tid == 0 && pipe_nops < pipe::MAX_OPS) {
+          pipe::Mail<N>& M = pipe::mail<N>();
+          M.op[pipe_nops] = code;
+          M.dst[pipe_nops] = dst;
+        }
+        pipe_nops += 1;
+      }
+    };
     auto ck_time = [&](long long k) { return a.save_at[k < a.K ? k : a.K - 1]; };
     // wide mode, pass 3: everything the bookkeeping below does to the n x d mean arrays, in ONE
     // sweep over the owned columns (reads the old state, writes the new one).
@@ -1134,7 +1417,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
             for (int i = 0; i < N; ++i) {
               double acc = Wg[(size_t)i * wd + c];
 #pragma unroll
-              for (int k = 0; k < N; ++k) acc = fma(SBW(OFF_G + i * N + k), gnc[k], acc);
+              for (int k = 0; k < N; ++k) acc = fma(PIPE ? pipe_G1[i * N + k] : SBW(OFF_G + i * N + k), gnc[k], acc);
               gmc[i] = acc;
             }
           }
@@ -1152,13 +1435,15 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
             if (em != nullptr) em[(size_t)i * wd + c] = (em_src == 2) ? mext[i] : pend_old;
           }
         }
-        __syncthreads();
+        cta_sync();
       }
     };
     // wide slot layout: [G | (unused n) | Lam | L1 | g (n x d) | m1 (n x d)]; src 0: merged result of
     // this step, 1: identity, 2: the committed running conditional (shared memory)
     auto wide_store_factor = [&](double* dst, int src) {
-      if constexpr (WIDE) {
+      if constexpr (PIPE) {
+        pipe_op(src == 0 ? pipe::OP_STORE_MERGED : (src == 1 ? pipe::OP_STORE_IDENTITY : pipe::OP_STORE_RUNNING), dst);
+      } else if constexpr (WIDE) {
         if (tid == 0) {
 #pragma unroll
           for (int i = 0; i < N; ++i) {
@@ -1188,7 +1473,7 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
     auto wide_copy = [&](double* dst, const double* src, bool zero_src) {  // [n][d] arrays
       if constexpr (WIDE) {
         for (int e = tid; e < N * wd; e += THREADS) dst[e] = zero_src ? 0.0 : src[e];
-        __syncthreads();
+        cta_sync();
       }
     };
 
@@ -1212,6 +1497,10 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
       for (int i = 0; i < N; ++i) dst[OFF_G + i * N + i] = 1.0;
     };
     auto bw_commit = [&]() {  // running conditional <- merged result
+      if constexpr (PIPE) {
+        pipe_op(pipe::OP_COMMIT, nullptr);
+        return;
+      }
 #pragma unroll
       for (int i = 0; i < N; ++i) {
 #pragma unroll
@@ -1223,6 +1512,10 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
       }
     };
     auto bw_reset = [&]() {  // running conditional <- identity (A.2)
+      if constexpr (PIPE) {
+        pipe_op(pipe::OP_RESET, nullptr);
+        return;
+      }
 #pragma unroll
       for (int e = 0; e < Lay::BW; ++e) SBW(e) = 0.0;
 #pragma unroll
@@ -1444,6 +1737,10 @@ __global__ void __launch_bounds__(THREADS, PN_MINBLOCKS) pn_scalar_kernel(const 
       }
       k_next += 1;
       after_checkpoint(finished);
+    }
+    if constexpr (PIPE) {
+      if (tid == 0) pipe::mail<N>().nops = (pipe_nops < pipe::MAX_OPS) ? pipe_nops : pipe::MAX_OPS;
+      pipe::bar_arrive(pipe::BAR_ACT, THREADS + 32);
     }
     if constexpr (SLICE) {
       // the quantum boundaries of different members are staggered (b * 7919): lanes that started together
