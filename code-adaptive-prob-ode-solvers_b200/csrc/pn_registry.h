@@ -196,7 +196,7 @@ template <class Prob, int NU, int STRAT, int THREADS, int PIPE = 0>
 struct WideInstance {
   using Lay = Layout<NU + 1, 1>;
   static cudaError_t launch_solve(const SolveArgs& a, int grid, size_t smem, cudaStream_t s) {
-    pn_scalar_kernel<Prob, NU, STRAT, 1, 0, THREADS, 1, 0, PIPE><<<grid, THREADS + 32 * PIPE, smem, s>>>(a);
+    pn_scalar_kernel<Prob, NU, STRAT, 1, 0, THREADS, 1, 0, PIPE><<<grid, THREADS + 64 * PIPE, smem, s>>>(a);
     return cudaGetLastError();
   }
   static cudaError_t launch_smooth(const SmoothArgs& a, cudaStream_t s) {
@@ -237,7 +237,7 @@ struct WideInstance {
     e.N = NU + 1;
     // runtime dimension; -32: the one-warp-per-IVP build for large ensembles; -160: the build with a backward warp (PIPE)
     e.D = PIPE ? -(THREADS + 32) : ((THREADS == 128) ? 0 : -THREADS);
-    e.extra_threads = 32 * PIPE;
+    e.extra_threads = 64 * PIPE;  // an idle warp (keeps the backward warp off main warp 0's sub-partition) + the backward warp
     e.Q = Prob::Q;
     e.P = Prob::P;
     e.slot_doubles = Lay::BW + Lay::NT;  // factor part of a slot; + 2 n d per slot and 3 n d per member at run time

@@ -262,6 +262,11 @@ static __device__ __noinline__ bool slice_quantum_reached(const SolveArgs& a, do
   return ((n_att + b * 7919LL) & (q - 1)) == 0;
 }
 
+template <int V>
+struct IntTag {
+  static constexpr int value = V;
+};
+
 template <int N>
 struct Binom {
   // flipped Pascal matrix A1[i][j] = C(nu-i, nu-j)
@@ -381,10 +386,9 @@ constexpr int BAR_JOB = 1, BAR_X = 2, BAR_ACT = 3, BAR_MAIN = 4;
 enum : int { OP_COMMIT = 1, OP_RESET = 2, OP_STORE_MERGED = 3, OP_STORE_RUNNING = 4, OP_STORE_IDENTITY = 5 };
 constexpr int MAX_OPS = 24;
 PN_DEV void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-PN_DEV void bar_arrive(int id, int count) {
-  __threadfence_block();
-  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
+// (shared-memory stores of the arriving thread are ordered before the completion of the barrier: the
+// producer / consumer use of named barriers, no fence needed)
+PN_DEV void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 template <int N>
 struct Mail {
   static constexpr int NT = N * (N + 1) / 2;
@@ -399,6 +403,9 @@ struct Mail {
   double X[N * N];         // X = RY^{-1} R12
   int cur;                 // which buffer of R holds the running conditional
   double R[2][N * N + NT]; // running conditional [G | Lam packed]; the other buffer receives the merged one
+  double gain[N];          // main warp 0 -> the other main warps
+  unsigned long long* stats;  // PN_PIPE_STATS builds: the workspace header's statistics words
+  double red[2][8];        // main warps: warp sums of a CTA reduction, double-buffered (one barrier per reduction)
   // bookkeeping: main warps -> backward warp (written before BAR_ACT)
   int nops;
   int op[MAX_OPS];
@@ -426,10 +433,29 @@ __device__ __noinline__ void backward_warp(Mail<N>& M, const int nmain) {
       dst[e] = (R == nullptr) ? ((e < N * N && (e / N) == (e % N)) ? 1.0 : 0.0)
                               : ((e < N * N) ? R[e] : ((e < OFF_LAM) ? 0.0 : R[N * N + (e - OFF_LAM)]));
   };
+#ifdef PN_PIPE_STATS
+  long long st_job = 0, st_act = 0, st_c0 = 0, st_x = 0, st_merge = 0;
+#define PN_PIPE_T0() st_c0 = clock64()
+#define PN_PIPE_T1(acc) acc += clock64() - st_c0
+#else
+#define PN_PIPE_T0()
+#define PN_PIPE_T1(acc)
+#endif
   for (;;) {
+    PN_PIPE_T0();
     bar_sync(BAR_JOB, total);
+    PN_PIPE_T1(st_job);
+#ifdef PN_PIPE_STATS
+    if (M.exit_ && lane == 0 && M.stats) {
+      atomicAdd(M.stats + 9, (unsigned long long)st_job);
+      atomicAdd(M.stats + 10, (unsigned long long)st_act);
+      atomicAdd(M.stats + 12, (unsigned long long)st_x);
+      atomicAdd(M.stats + 13, (unsigned long long)st_merge);
+    }
+#endif
     if (M.exit_) return;
     if (M.reset) set_identity(M.R[cur]);
+    PN_PIPE_T0();
     double BL[N][N], BR[N][N], R12[N][N], RY[N][N], v0[N], gg[N], p[N], pinv[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
@@ -482,6 +508,8 @@ __device__ __noinline__ void backward_warp(Mail<N>& M, const int nmain) {
       M.cur = cur;
     }
     bar_arrive(BAR_X, total);
+    PN_PIPE_T1(st_x);
+    PN_PIPE_T0();
     // new conditional (un-preconditioned) and the merge with the running one (A.4)
     double Gn[N][N], Ln[N][N];
 #pragma unroll
@@ -553,8 +581,11 @@ __device__ __noinline__ void backward_warp(Mail<N>& M, const int nmain) {
         for (int j = 0; j <= i; ++j) Rn[N * N + Lay::tri(i, j)] = Mt[j][i];  // merged Lam (lower)
     }
     __syncwarp();
+    PN_PIPE_T1(st_merge);
     // what the bookkeeping of this iteration decided
+    PN_PIPE_T0();
     bar_sync(BAR_ACT, total);
+    PN_PIPE_T1(st_act);
     const int nops = M.nops;
     for (int o = 0; o < nops; ++o) {
       const int op = M.op[o];
@@ -589,7 +620,7 @@ __device__ __noinline__ void backward_warp(Mail<N>& M, const int nmain) {
 //           memory (L2 resident) and each thread owns the columns c = tid, tid + THREADS, ...;
 //           norms are reduced over the CTA.  Prob::D is a dummy (1) in this mode.
 template <class Prob, int NU, int STRAT, int GROUP, int BDIAG, int THREADS, int WIDE = 0, int SLICE = 0, int PIPE = 0>
-__global__ void __launch_bounds__(THREADS + 32 * PIPE, PIPE ? 1 : PN_MINBLOCKS) pn_scalar_kernel(const __grid_constant__ SolveArgs a) {
+__global__ void __launch_bounds__(THREADS + 64 * PIPE, PIPE ? 1 : PN_MINBLOCKS) pn_scalar_kernel(const __grid_constant__ SolveArgs a) {
   constexpr int N = NU + 1, DT = Prob::D, D = (GROUP > 1) ? 1 : DT, Q = Prob::Q, P = (Prob::P > 0 ? Prob::P : 1);
   constexpr int DV = (GROUP > 1) ? DT : 1;  // lanes ("virtual members") per IVP that own state
   static_assert(GROUP == 1 || (GROUP >= DT && (GROUP & (GROUP - 1)) == 0 && GROUP <= 32), "bad GROUP");
@@ -600,17 +631,49 @@ __global__ void __launch_bounds__(THREADS + 32 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
   constexpr double TIME_EPS = 10.0 * 2.220446049250313e-16;
   static_assert(!PIPE || (WIDE && STRAT == 1 && GROUP == 1), "PIPE: CTA-per-IVP kernel with the fixed-point strategy");
   if constexpr (PIPE) {
-    if (threadIdx.x >= THREADS) {  // the backward warp
-      pipe::backward_warp<N>(pipe::mail<N>(), THREADS);
+    // warps 0 .. THREADS/32 - 1: main; the next warp exits at once (warp w runs on sub-partition w mod 4: the
+    // backward warp must not share the fp64 pipe of main warp 0, the one that carries the factor arithmetic);
+    // the last warp is the backward warp
+    if (threadIdx.x >= THREADS) {
+      if (threadIdx.x >= THREADS + 32) pipe::backward_warp<N>(pipe::mail<N>(), THREADS);
       return;
     }
   }
+  // PIPE: the n x n factor arithmetic of the filter path runs on main warp 0 only (the other main warps sweep
+  // their mean columns and get the gain through shared memory): sub-partitions 1 .. 3 stay free for the
+  // backward warp.  Otherwise every thread carries it.
+  const bool pipe_F = !PIPE || (threadIdx.x < 32);
   // barrier over the threads that run the step (PIPE: the main warps only)
   auto cta_sync = [&]() {
     if constexpr (PIPE) pipe::bar_sync(pipe::BAR_MAIN, THREADS); else __syncthreads();
   };
   bool pipe_reset = false;  // PIPE: the next job is the first of a member
   int pipe_nops = 0;        // PIPE: ops queued for the backward warp in this iteration
+  int pipe_red_phase = 0;   // PIPE: which reduction scratch buffer the next CTA reduction uses
+  // PIPE: the checkpoint time the bookkeeping compares with, kept in a register between checkpoints (every
+  // iteration asked global memory for it twice, in the middle of the serial part of the step)
+  long long pipe_ck_k = -1;
+  double pipe_ck_t = 0.0;
+  auto ck_cached = [&](long long k) -> double {
+    const long long kc = k < a.K ? k : a.K - 1;
+    if constexpr (PIPE) {
+      if (kc != pipe_ck_k) {
+        pipe_ck_k = kc;
+        pipe_ck_t = a.save_at[kc];
+      }
+      return pipe_ck_t;
+    } else {
+      return a.save_at[kc];
+    }
+  };
+#ifdef PN_PIPE_STATS
+  long long pipe_tm = clock64();
+#define PN_MAIN_PHASE(w) do { if (PIPE && tid == 0) { const long long now_ = clock64(); atomicAdd(a.ticket + (w), (unsigned long long)(now_ - pipe_tm)); pipe_tm = now_; } } while (0)
+#else
+#define PN_MAIN_PHASE(w) do { } while (0)
+#endif
+  // PIPE: preconditioner of the step the controller proposes, computed one iteration ahead (off the head of the chain)
+  double pipe_spec_dt = __longlong_as_double(0x7ff8000000000000LL), pipe_spec_p[N], pipe_spec_pinv[N];
 
   extern __shared__ double smem[];
   // [element][thread]
@@ -651,6 +714,18 @@ __global__ void __launch_bounds__(THREADS + 32 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
     // fixed order: per-warp butterfly, then the warp sums added in warp order
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, off);
+    if constexpr (PIPE) {
+      // alternating scratch buffers: the barrier of the NEXT reduction separates this one's reads from the
+      // writes of the one after it
+      double* rb = pipe::mail<N>().red[pipe_red_phase];
+      pipe_red_phase ^= 1;
+      if ((tid & 31) == 0) rb[tid >> 5] = v;
+      cta_sync();
+      double r = rb[0];
+#pragma unroll
+      for (int w = 1; w < THREADS / 32; ++w) r = r + rb[w];
+      return r;
+    }
     cta_sync();
     if ((tid & 31) == 0) s_red[tid >> 5] = v;
     cta_sync();
@@ -886,6 +961,7 @@ __global__ void __launch_bounds__(THREADS + 32 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
       continue;
     }
     stat_warp_iters += 1;
+    PN_MAIN_PHASE(14);  // end of the previous iteration's tail / member fetch
     if constexpr (SLICE) {
       // belt and braces: every warp re-derives the queue mask from the counters once in a while, so a
       // parked member could not stay invisible even if no warp ever ran completely out of work
@@ -897,7 +973,7 @@ __global__ void __launch_bounds__(THREADS + 32 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
     if (!have) continue;  // idle lane
 
     // ---- choose this iteration's prediction --------------------------------------------
-    double t_ck = a.save_at[k_next < a.K ? k_next : a.K - 1];
+    double t_ck = ck_cached(k_next);
     double dt, sigma_given;
     if (mode == MODE_STEP) {
       dt = (a.flags & FLAG_FIXED_GRID) ? (t_ck - t) : dt_next;
@@ -913,19 +989,33 @@ __global__ void __launch_bounds__(THREADS + 32 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
     // ==================== uber step (straight-line, identical for all lanes) ============
     // A.1 preconditioner
     double p[N], pinv[N];
-    {
-      double adt = fabs(dt);
+    auto precondition = [&](double dt_, double (&p_)[N], double (&pinv_)[N]) {
+      double adt = fabs(dt_);
       double sq = dsqrt(adt);
       double isq = rcp(sq), idt = rcp(adt);
       double dtp = 1.0, idtp = 1.0;
 #pragma unroll
       for (int k = 0; k <= NU; ++k) {
         const int i = NU - k;
-        p[i] = (sq * dtp) * (1.0 / factorial(k));
-        pinv[i] = (isq * idtp) * factorial(k);
+        p_[i] = (sq * dtp) * (1.0 / factorial(k));
+        pinv_[i] = (isq * idtp) * factorial(k);
         dtp *= adt;
         idtp *= idt;
       }
+    };
+    if constexpr (PIPE) {
+      // the previous iteration has already worked this out beside its controller chain if it guessed the step right
+      if (dt == pipe_spec_dt) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          p[i] = pipe_spec_p[i];
+          pinv[i] = pipe_spec_pinv[i];
+        }
+      } else {
+        precondition(dt, p, pinv);
+      }
+    } else {
+      precondition(dt, p, pinv);
     }
     // predicted mean
     double m_p[N][D], m_ext_p[N][D], m_ext[N][D];
@@ -977,17 +1067,34 @@ __global__ void __launch_bounds__(THREADS + 32 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
     // form the residual z (kept in shared memory) and the CTA-wide sum of squares
     double wide_zz = 0.0;
     if constexpr (WIDE) {
-      for (int c = tid; c < wd; c += THREADS) {
-        double mp[N];
+      {
+        // (PIPE: two columns at a time, loads first -- see pass 3)
+        auto cols = [&](auto nc_tag, int c0) {
+          constexpr int NC = decltype(nc_tag)::value;
+          double mo[NC][N];
 #pragma unroll
-        for (int i = 0; i < N; ++i) mp[i] = pinv[i] * Wm[(size_t)i * wd + c];
-        double e0 = mp[0], e1 = mp[1];
+          for (int u = 0; u < NC; ++u)
 #pragma unroll
-        for (int j = 1; j < N; ++j) e0 = fma(Binom<N>::at(0, j), mp[j], e0);
+            for (int i = 0; i < N; ++i) mo[u][i] = Wm[(size_t)i * wd + c0 + u * THREADS];
 #pragma unroll
-        for (int j = 2; j < N; ++j) e1 = fma(Binom<N>::at(1, j), mp[j], e1);
-        s_ubuf[c] = p[0] * e0;
-        s_zbuf[c] = p[1] * e1;  // m_ext[q = 1][c] for now
+          for (int u = 0; u < NC; ++u) {
+            double mp[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) mp[i] = pinv[i] * mo[u][i];
+            double e0 = mp[0], e1 = mp[1];
+#pragma unroll
+            for (int j = 1; j < N; ++j) e0 = fma(Binom<N>::at(0, j), mp[j], e0);
+#pragma unroll
+            for (int j = 2; j < N; ++j) e1 = fma(Binom<N>::at(1, j), mp[j], e1);
+            s_ubuf[c0 + u * THREADS] = p[0] * e0;
+            s_zbuf[c0 + u * THREADS] = p[1] * e1;  // m_ext[q = 1][c] for now
+          }
+        };
+        int c = tid;
+        if constexpr (PIPE) {
+          for (; c + THREADS < wd; c += 2 * THREADS) cols(IntTag<2>{}, c);
+        }
+        for (; c < wd; c += THREADS) cols(IntTag<1>{}, c);
       }
       cta_sync();
       const double cc = par[0] * (double)((wN + 1) * (wN + 1));
@@ -1008,6 +1115,7 @@ __global__ void __launch_bounds__(THREADS + 32 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
         s_zbuf[c] = zc;  // own column only: no hazard
       }
       wide_zz = block_sum(acc);
+      PN_MAIN_PHASE(15);  // preconditioner + pass 1
     }
     // local calibration + error estimate from the process noise
     double err, sigma;
@@ -1043,7 +1151,7 @@ __global__ void __launch_bounds__(THREADS + 32 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
     double Gn[N][N], gn[N][D];  // new conditional (un-preconditioned); Lam_n lower
     double Ln[N][N];
     double X[N][N];             // RY^{-1} R12 (fixed-point); G_p = X^T
-    {
+    if (pipe_F) {
       double L_p[N][N];  // lower
 #pragma unroll
       for (int i = 0; i < N; ++i)
@@ -1120,7 +1228,7 @@ __global__ void __launch_bounds__(THREADS + 32 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
         for (int j = 0; j <= i; ++j) L_ext[i][j] = p[i] * RY[j][i];
       if constexpr (PIPE) {
         // hand the reflectors to the backward warp (one main warp writes: every thread holds the same values)
-        if (tid < 32) {
+        {
           pipe::Mail<N>& M = pipe::mail<N>();
 #pragma unroll
           for (int i = 0; i < N; ++i) {
@@ -1137,9 +1245,8 @@ __global__ void __launch_bounds__(THREADS + 32 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
           }
           M.reset = pipe_reset ? 1 : 0;
           M.exit_ = 0;
+          M.stats = a.ticket;
         }
-        pipe_reset = false;
-        pipe::bar_arrive(pipe::BAR_JOB, THREADS + 32);
       }
       if (FIX && !PIPE) {
         // The lower-right block BR is NOT triangularised: BR^T is already a valid square-root factor
@@ -1172,6 +1279,11 @@ __global__ void __launch_bounds__(THREADS + 32 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
           for (int j = 0; j < N; ++j) Ln[i][j] = p[i] * BR[j][i];
         }
       }
+    }
+    if constexpr (PIPE) {
+      pipe_reset = false;
+      pipe::bar_arrive(pipe::BAR_JOB, THREADS + 32);  // (all main threads arrive; warp 0 wrote the job)
+      PN_MAIN_PHASE(16);  // calibration + predict QR + publish
     }
     // Program order of the two blocks that are off the step-size chain (merge of the backward conditional,
     // QR of the corrected factor).  Thread-per-IVP kernels run them AFTER the error norm and the PI
@@ -1290,6 +1402,7 @@ __global__ void __launch_bounds__(THREADS + 32 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
       for (int j = 0; j <= i; ++j) L_new[i][j] = (j <= Q) ? Mc[j][i] : L_ext[i][j];
     };
     {
+      if (pipe_F) {
       double S = 0.0;
 #pragma unroll
       for (int j = 0; j <= Q; ++j) {
@@ -1308,7 +1421,19 @@ __global__ void __launch_bounds__(THREADS + 32 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
         for (int j = 0; j <= ((i < Q) ? i : Q); ++j) acc = fma(L_ext[i][j], hL[j], acc);
         gain[i] = acc * invS;
       }
-      if constexpr (!LATE_BLOCKS) corrected_factor();
+      }
+      if constexpr (PIPE) {
+        // main warp 0 -> the other main warps: the gain (all they need of the factor arithmetic)
+        pipe::Mail<N>& M = pipe::mail<N>();
+        if (pipe_F) {
+#pragma unroll
+          for (int i = 0; i < N; ++i) M.gain[i] = gain[i];
+        }
+        cta_sync();
+#pragma unroll
+        for (int i = 0; i < N; ++i) gain[i] = M.gain[i];
+      }
+      if constexpr (!LATE_BLOCKS && !PIPE) corrected_factor();
 #pragma unroll
       for (int i = 0; i < N; ++i)
 #pragma unroll
@@ -1317,12 +1442,27 @@ __global__ void __launch_bounds__(THREADS + 32 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
       if constexpr (WIDE) {
         // pass 2: proposed u = m_new[0][c] = m_ext[0][c] - gain[0] z[c] per owned column
         double part = 0.0;
-        for (int c = tid; c < wd; c += THREADS) {
-          const double u_new = fma(-gain[0], s_zbuf[c], s_ubuf[c]);
-          const double ratio = err * rcp(fma(rtol, fabs(u_new), atol));
-          part = fma(ratio, ratio, part);
+        {
+          int c = tid;
+          if constexpr (PIPE) {
+            // two reciprocal chains in flight; the partial sum still takes the columns in ascending order
+            for (; c + THREADS < wd; c += 2 * THREADS) {
+              const double ua = fma(-gain[0], s_zbuf[c], s_ubuf[c]);
+              const double ub = fma(-gain[0], s_zbuf[c + THREADS], s_ubuf[c + THREADS]);
+              const double ra = err * rcp(fma(rtol, fabs(ua), atol));
+              const double rb = err * rcp(fma(rtol, fabs(ub), atol));
+              part = fma(ra, ra, part);
+              part = fma(rb, rb, part);
+            }
+          }
+          for (; c < wd; c += THREADS) {
+            const double u_new = fma(-gain[0], s_zbuf[c], s_ubuf[c]);
+            const double ratio = err * rcp(fma(rtol, fabs(u_new), atol));
+            part = fma(ratio, ratio, part);
+          }
         }
         acc = block_sum(part);
+        PN_MAIN_PHASE(17);  // correction + gain broadcast + pass 2
       } else if (GROUP == 1) {
 #pragma unroll
         for (int c = 0; c < D; ++c) {
@@ -1334,6 +1474,11 @@ __global__ void __launch_bounds__(THREADS + 32 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
         acc = group_sum<GROUP>(real ? fma(ratio, ratio, 0.0) : 0.0, gmask);
       }
       e_norm = dsqrt(acc) * inv_sqrt_d;
+    }
+    // PIPE: the corrected factor's Householder chain sits beside the controller's sqrt -> log -> exp chain (two
+    // independent serial chains in one basic block) instead of in front of the error norm's CTA reduction
+    if constexpr (PIPE) {
+      if (pipe_F) corrected_factor();
     }
     // PI controller
     double fac, le_now;
@@ -1351,21 +1496,34 @@ __global__ void __launch_bounds__(THREADS + 32 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
       corrected_factor();
       merge_running_conditional();
     }
+    if constexpr (PIPE) {
+      pipe_spec_dt = fac * dt;  // = dt_next of an attempted step (the bookkeeping below forms the same product)
+      precondition(pipe_spec_dt, pipe_spec_p, pipe_spec_pinv);
+    }
     // ==================== per-lane bookkeeping (cheap, may diverge) =====================
     // helpers -------------------------------------------------------------------------
     // PIPE: the backward warp has published X by now (it is busy with the merge); the running G the offset
     // update needs is the buffer it is NOT writing.  Everything the bookkeeping below wants done to the
     // running conditional is queued as an op and handed over in one piece (BAR_ACT).
-    const double* pipe_G1 = nullptr;
+    const double* pipe_G1 = nullptr;  // PIPE: the running G (before this step's merge) and X, in shared memory
+    const double* pipe_X = nullptr;
     if constexpr (PIPE) {
+      PN_MAIN_PHASE(18);  // error norm + corrected factor + controller
+#ifdef PN_PIPE_STATS
+      const long long pipe_c0 = clock64();
+#endif
       pipe::bar_sync(pipe::BAR_X, THREADS + 32);
+#ifdef PN_PIPE_STATS
+      if (tid == 0) {
+        atomicAdd(a.ticket + 8, (unsigned long long)(clock64() - pipe_c0));
+        atomicAdd(a.ticket + 11, 1ULL);
+      }
+#endif
       const pipe::Mail<N>& M = pipe::mail<N>();
-#pragma unroll
-      for (int i = 0; i < N; ++i)
-#pragma unroll
-        for (int c = 0; c < N; ++c) X[i][c] = M.X[i * N + c];
+      pipe_X = M.X;
       pipe_G1 = M.R[M.cur];
       pipe_nops = 0;
+      PN_MAIN_PHASE(20);  // X wait + load
     }
     auto pipe_op = [&](int code, double* dst) {
       if constexpr (PIPE) {
@@ -1377,7 +1535,7 @@ __global__ void __launch_bounds__(THREADS + 32 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
         pipe_nops += 1;
       }
     };
-    auto ck_time = [&](long long k) { return a.save_at[k < a.K ? k : a.K - 1]; };
+    auto ck_time = [&](long long k) { return ck_cached(k); };
     // wide mode, pass 3: everything the bookkeeping below does to the n x d mean arrays, in ONE
     // sweep over the owned columns (reads the old state, writes the new one).
     //   mw: what becomes the state mean   (0 keep, 1 m_new, 2 m_ext, 3 pending mean)
@@ -1387,54 +1545,77 @@ __global__ void __launch_bounds__(THREADS + 32 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
     //   em_src: 2 m_ext, 3 pending mean
     auto wide_pass3 = [&](int mw, int gw, bool pw, double* eg, double* em, int em_src) {
       if constexpr (WIDE) {
-        for (int c = tid; c < wd; c += THREADS) {
-          double mo[N], mp[N], mep[N], mext[N];
+        // NC columns at a time: all loads first, then the arithmetic, then the stores -- the arrays may alias as
+        // far as the compiler knows, so a column-by-column loop serialises on its own stores (PIPE build: 2)
+        auto cols = [&](auto nc_tag, int c0) {
+          constexpr int NC = decltype(nc_tag)::value;
+          double mo[NC][N], wg[NC][N], pend_old[NC][N], zc[NC];
 #pragma unroll
-          for (int i = 0; i < N; ++i) {
-            mo[i] = Wm[(size_t)i * wd + c];
-            mp[i] = pinv[i] * mo[i];
+          for (int u = 0; u < NC; ++u) {
+            const int c = c0 + u * THREADS;
+            zc[u] = s_zbuf[c];
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+              mo[u][i] = Wm[(size_t)i * wd + c];
+              wg[u][i] = (FIX && (gw == 1 || eg != nullptr)) ? Wg[(size_t)i * wd + c] : 0.0;
+              pend_old[u][i] = (mw == 3 || em_src == 3) ? Wp[(size_t)i * wd + c] : 0.0;
+            }
           }
+          double mext[NC][N], gmc[NC][N], mn[NC][N];
 #pragma unroll
-          for (int i = 0; i < N; ++i) {
-            double acc = mp[i];
+          for (int u = 0; u < NC; ++u) {
+            double mp[N], mep[N];
 #pragma unroll
-            for (int j = i + 1; j < N; ++j) acc = fma(Binom<N>::at(i, j), mp[j], acc);
-            mep[i] = acc;
-            mext[i] = p[i] * acc;
-          }
-          const double zc = s_zbuf[c];
-          double gmc[N];
-          if (FIX && (gw == 1 || eg != nullptr)) {
-            double gnc[N];
+            for (int i = 0; i < N; ++i) mp[i] = pinv[i] * mo[u][i];
 #pragma unroll
             for (int i = 0; i < N; ++i) {
               double acc = mp[i];
 #pragma unroll
-              for (int k = 0; k < N; ++k) acc = fma(-X[k][i], mep[k], acc);
-              gnc[i] = p[i] * acc;
+              for (int j = i + 1; j < N; ++j) acc = fma(Binom<N>::at(i, j), mp[j], acc);
+              mep[i] = acc;
+              mext[u][i] = p[i] * acc;
             }
+            if (FIX && (gw == 1 || eg != nullptr)) {
+              double gnc[N];
+#pragma unroll
+              for (int i = 0; i < N; ++i) {
+                double acc = mp[i];
+#pragma unroll
+                for (int k = 0; k < N; ++k) acc = fma(PIPE ? -pipe_X[k * N + i] : -X[k][i], mep[k], acc);
+                gnc[i] = p[i] * acc;
+              }
+#pragma unroll
+              for (int i = 0; i < N; ++i) {
+                double acc = wg[u][i];
+#pragma unroll
+                for (int k = 0; k < N; ++k) acc = fma(PIPE ? pipe_G1[i * N + k] : SBW(OFF_G + i * N + k), gnc[k], acc);
+                gmc[u][i] = acc;
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < N; ++i) mn[u][i] = fma(-gain[i], zc[u], mext[u][i]);
+          }
+#pragma unroll
+          for (int u = 0; u < NC; ++u) {
+            const int c = c0 + u * THREADS;
 #pragma unroll
             for (int i = 0; i < N; ++i) {
-              double acc = Wg[(size_t)i * wd + c];
-#pragma unroll
-              for (int k = 0; k < N; ++k) acc = fma(PIPE ? pipe_G1[i * N + k] : SBW(OFF_G + i * N + k), gnc[k], acc);
-              gmc[i] = acc;
+              if (pw) Wp[(size_t)i * wd + c] = mn[u][i];
+              if (mw == 1) Wm[(size_t)i * wd + c] = mn[u][i];
+              if (mw == 2) Wm[(size_t)i * wd + c] = mext[u][i];
+              if (mw == 3) Wm[(size_t)i * wd + c] = pend_old[u][i];
+              if (FIX && gw == 1) Wg[(size_t)i * wd + c] = gmc[u][i];
+              if (FIX && gw == 2) Wg[(size_t)i * wd + c] = 0.0;
+              if (FIX && eg != nullptr) eg[(size_t)i * wd + c] = gmc[u][i];
+              if (em != nullptr) em[(size_t)i * wd + c] = (em_src == 2) ? mext[u][i] : pend_old[u][i];
             }
           }
-#pragma unroll
-          for (int i = 0; i < N; ++i) {
-            const double mn = fma(-gain[i], zc, mext[i]);
-            const double pend_old = (mw == 3 || em_src == 3) ? Wp[(size_t)i * wd + c] : 0.0;
-            if (pw) Wp[(size_t)i * wd + c] = mn;
-            if (mw == 1) Wm[(size_t)i * wd + c] = mn;
-            if (mw == 2) Wm[(size_t)i * wd + c] = mext[i];
-            if (mw == 3) Wm[(size_t)i * wd + c] = pend_old;
-            if (FIX && gw == 1) Wg[(size_t)i * wd + c] = gmc[i];
-            if (FIX && gw == 2) Wg[(size_t)i * wd + c] = 0.0;
-            if (FIX && eg != nullptr) eg[(size_t)i * wd + c] = gmc[i];
-            if (em != nullptr) em[(size_t)i * wd + c] = (em_src == 2) ? mext[i] : pend_old;
-          }
+        };
+        int c = tid;
+        if constexpr (PIPE) {
+          for (; c + THREADS < wd; c += 2 * THREADS) cols(IntTag<2>{}, c);
         }
+        for (; c < wd; c += THREADS) cols(IntTag<1>{}, c);
         cta_sync();
       }
     };
@@ -1653,6 +1834,7 @@ __global__ void __launch_bounds__(THREADS + 32 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
             mode = MODE_INTERP_A;
           } else {
             wide_pass3(1, FIX ? 1 : 0, false, nullptr, nullptr, 0);  // before bw_commit: needs the old G
+            PN_MAIN_PHASE(21);  // pass 3 of an accepted step
             t = t1;
             sigma_state = sigma;
 #pragma unroll
@@ -1662,9 +1844,13 @@ __global__ void __launch_bounds__(THREADS + 32 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
 #pragma unroll
               for (int j = 0; j <= i; ++j) SL(i, j) = L_new[i][j];
             }
+            PN_MAIN_PHASE(22);  // state parked
+            PN_MAIN_PHASE(23);  // (empty: the cost of a marker)
             if (FIX) bw_commit();
             record(t1, m_new, L_new);
+            PN_MAIN_PHASE(24);  // commit op + record
             resolve_hits(finished);
+            PN_MAIN_PHASE(25);  // resolve_hits
           }
         } else {
           n_rej += 1;
@@ -1720,7 +1906,7 @@ __global__ void __launch_bounds__(THREADS + 32 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
       if constexpr (WIDE) {
         const bool term = (k_next == a.K - 1);
         const double t1p = SPEND(0);
-        const bool again = (k_next + 1 < a.K) && (t1p > ck_time(k_next + 1) + TIME_EPS);
+        const bool again = (k_next + 1 < a.K) && (t1p > a.save_at[k_next + 1] + TIME_EPS);
         if (term) {
           wide_store_factor(wcond, 0);
           wide_store_L1(wcond, 1);
@@ -1741,6 +1927,7 @@ __global__ void __launch_bounds__(THREADS + 32 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
     if constexpr (PIPE) {
       if (tid == 0) pipe::mail<N>().nops = (pipe_nops < pipe::MAX_OPS) ? pipe_nops : pipe::MAX_OPS;
       pipe::bar_arrive(pipe::BAR_ACT, THREADS + 32);
+      PN_MAIN_PHASE(19);  // X wait + pass 3 + bookkeeping
     }
     if constexpr (SLICE) {
       // the quantum boundaries of different members are staggered (b * 7919): lanes that started together
