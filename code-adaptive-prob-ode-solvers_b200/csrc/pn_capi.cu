@@ -177,6 +177,7 @@ __global__ void pn_order_scatter_kernel(const double* tol, long long B, unsigned
   if (i < B) order[atomicAdd(&cursor[order_bucket(tol[2 * i], tol[2 * i + 1])], 1u)] = i;
 }
 
+constexpr long long PAIR_MAX_BATCH = 148 * 128;  // thread-per-IVP PAIR build: one 128-lane CTA per SM
 constexpr long long WIDE_WARP_MIN_BATCH = 592;  // CTA-per-IVP isotropic family: one warp per IVP from four members per SM on
 constexpr long long COOP_MAX_BATCH = 0;        // largest ensemble the cooperative scalar kernel is chosen for (0: opt-in only)
 constexpr long long DENSE_CTA_MAX_CTAS = 296;  // per-CTA scratch regions the workspace provides (2 per SM of a B200)
@@ -215,6 +216,19 @@ static int resolve(const pn_b200_desc* d, const KernelEntry** out) {
     if (d->batch <= coop_max) {
       const KernelEntry* kc = find_kernel(FAMILY_COOP, d->problem, d->nu, d->strategy, d->d);
       if (kc) k = kc;
+    }
+  }
+  // Small ensembles of the thread-per-IVP family, fixed-point strategy: filter lane + backward lane per IVP
+  // (PAIR build) while the members fit one filter warp per SM sub-partition (PN_B200_PAIR=0 switches it off,
+  // PN_B200_PAIR_MAX_BATCH=<members> moves the limit; results are bit-identical either way)
+  if (k && k->family == FAMILY_SCALAR && d->strategy == PN_B200_FIXEDPOINT && d->calibration != PN_B200_CALIB_MLE &&
+      !(d->flags & PN_B200_FLAG_RECORD)) {
+    const char* pe = getenv("PN_B200_PAIR");
+    long long pair_max = PAIR_MAX_BATCH;
+    if (const char* e = getenv("PN_B200_PAIR_MAX_BATCH")) pair_max = atoll(e);
+    if (!(pe && pe[0] == '0') && d->batch <= pair_max) {
+      const KernelEntry* kp = find_kernel(FAMILY_PAIR, d->problem, d->nu, d->strategy, d->d);
+      if (kp) k = kp;
     }
   }
   // lane-per-dimension family: blockdiag EKF0, and isotropic EKF0 for problems too wide for one thread

@@ -21,7 +21,8 @@ enum : int {
   FAMILY_WIDE = 4,        // CTA per IVP, isotropic, runtime dimension (Brusselator d = 2N up to 4096)
   FAMILY_DENSE_ROWS = 5,  // 16 or 32 lanes per IVP, register-resident Householder columns (dense, D <= 32)
   FAMILY_DENSE_CTA = 6,   // CTA per IVP, dense with a large runtime dimension, blocked QR on the FP64 tensor path
-  FAMILY_COOP = 7         // n lanes per IVP (scalar ODEs, small ensembles): columns of every QR spread over the lanes
+  FAMILY_COOP = 7,        // n lanes per IVP (scalar ODEs, small ensembles): columns of every QR spread over the lanes
+  FAMILY_PAIR = 8         // thread per IVP + a backward lane per IVP in a partner warp (fixed-point, small ensembles)
 };
 inline bool family_is_dense(int family) { return family == FAMILY_DENSE || family == FAMILY_DENSE_ROWS; }
 
@@ -276,6 +277,32 @@ struct CoopInstance {
   }
 };
 
+// thread-per-IVP kernels for small ensembles: THREADS filter lanes + THREADS backward lanes per CTA (PAIR = 1);
+// same slots / smoothing / sampling / likelihood kernels as the thread-per-IVP family
+template <class Prob, int NU, int THREADS>
+struct PairInstance {
+  using Base = ScalarInstance<Prob, NU, 1, 1, 0, 128>;
+  using Lay = Layout<NU + 1, Prob::D>;
+  using MB = pair::Mailbox<NU + 1, Prob::D>;
+  static cudaError_t launch_solve(const SolveArgs& a, int grid, size_t smem, cudaStream_t s) {
+    pn_scalar_kernel<Prob, NU, 1, 1, 0, THREADS, 0, 0, 0, 1><<<grid, 2 * THREADS, smem, s>>>(a);
+    return cudaGetLastError();
+  }
+  static KernelEntry entry() {
+    KernelEntry e = Base::entry();
+    e.family = FAMILY_PAIR;
+    e.threads = THREADS;
+    e.extra_threads = THREADS;
+    e.smem_doubles = Lay::BW + Lay::PEND + Lay::MARG + MB::DOUBLES + (MB::INTS + 1) / 2;  // per filter lane
+    e.ctx_doubles = 0;
+    e.solve_func_sliced = nullptr;
+    e.launch_solve_sliced = nullptr;
+    e.solve_func = (const void*)&pn_scalar_kernel<Prob, NU, 1, 1, 0, THREADS, 0, 0, 0, 1>;
+    e.launch_solve = &launch_solve;
+    return e;
+  }
+};
+
 // dense factorisation with a large runtime dimension: CTA per IVP, blocked Householder QR + DMMA products
 template <class Prob, int NU, int STRAT, int NB, int MINB>
 struct DenseCtaInstance {
@@ -341,6 +368,8 @@ struct Registrar {
   static ::pn::Registrar PN_CAT(pn_reg_, __COUNTER__)(::pn::DenseInstance<::pn::Prob, NU, STRAT, WARPS>::entry())
 #define PN_REGISTER_DENSE_ROWS(Prob, NU, STRAT, LANES, WARPS) \
   static ::pn::Registrar PN_CAT(pn_reg_, __COUNTER__)(::pn::DenseRowsInstance<::pn::Prob, NU, STRAT, LANES, WARPS>::entry())
+#define PN_REGISTER_PAIR(Prob, NU) \
+  static ::pn::Registrar PN_CAT(pn_reg_, __COUNTER__)(::pn::PairInstance<::pn::Prob, NU, 128>::entry())
 #define PN_REGISTER_COOP(Prob, NU, STRAT) \
   static ::pn::Registrar PN_CAT(pn_reg_, __COUNTER__)(::pn::CoopInstance<::pn::Prob, NU, STRAT, 128>::entry())
 #define PN_REGISTER_DENSE_CTA(Prob, NU, STRAT, NB, MINB) \

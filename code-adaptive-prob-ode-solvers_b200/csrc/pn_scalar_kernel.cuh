@@ -607,6 +607,250 @@ __device__ __noinline__ void backward_warp(Mail<N>& M, const int nmain) {
 }
 }  // namespace pipe
 
+
+// ---- PAIR = 1 (thread-per-IVP kernels, fixed-point strategy, small ensembles): the backward warp idea of the
+// PIPE build, lane by lane.  Below ~19k members every SM sub-partition holds at most one warp of the
+// thread-per-IVP kernel and the launch takes 16k steps x the latency of ONE step whatever the ensemble size
+// (DESIGN 3.6).  Here a CTA is THREADS "filter" lanes + THREADS "backward" lanes: lane l of filter warp w and
+// lane l of backward warp w serve the same IVP.  The filter lane keeps predict mean / left block of the predict
+// QR / correction / error norm / controller and the state; once per iteration it leaves the reflectors of the
+// predict QR and what its bookkeeping decided (a short op list) in a per-lane mailbox in shared memory.  The
+// backward lane -- one iteration behind -- applies the reflectors to the right block, solves for the smoothing
+// gain, forms the new conditional, merges it into the running one (which it owns) and executes the ops.  Two
+// named barriers per warp pair and iteration (job ready: filter arrives / backward waits; mailbox free: the
+// other way round).  Same operations in the same order as the PAIR = 0 kernel: bit-identical results.
+namespace pair {
+constexpr int MAX_OPS = 8;
+template <int N, int D>
+struct Mailbox {
+  static constexpr int NT = N * (N + 1) / 2;
+  // doubles per lane
+  static constexpr int O_BL = 0, O_V0 = O_BL + N * N, O_G = O_V0 + N, O_RY = O_G + N, O_LP = O_RY + NT, O_P = O_LP + NT,
+                       O_PINV = O_P + N, O_MP = O_PINV + N, O_MEP = O_MP + N * D, JOB_RAW = O_MEP + N * D,
+                       JOB = (JOB_RAW + 1) & ~1,  // the job travels as 16-byte pairs: [pair][lane][2]
+                       O_DST = JOB,               // op destinations: 64-bit pointers in double-sized cells, [cell][lane]
+                       DOUBLES = O_DST + 2 * MAX_OPS;
+  // The op list is double-buffered (parity of the iteration): the backward lane reads it AFTER its merge, when
+  // the filter lane may already be writing the next one; the job itself is taken out of the mailbox at once.
+  // ints per lane: [0] reset-before flag (part of the job), then per parity [number of ops, op codes ...]
+  static constexpr int INTS = 1 + 2 * (1 + MAX_OPS);
+  __host__ __device__ static constexpr int i_nops(int q) { return 1 + q * (1 + MAX_OPS); }
+  static constexpr int BYTES_PER_LANE = DOUBLES * 8 + INTS * 4;
+};
+
+template <int N, int D, int THREADS>
+__device__ __noinline__ void backward_lanes(double* s_bw, double* s_job, int* s_int, const volatile int* s_exit) {
+  using Lay = Layout<N, D>;
+  using MB = Mailbox<N, D>;
+  constexpr int OFF_G = 0, OFF_g = N * N, OFF_LAM = N * N + N * D;
+  const int l = threadIdx.x - THREADS, w = l >> 5;
+#define PBW(e) s_bw[(e) * THREADS + l]
+#define PJ(e) s_job[(e) * THREADS + l]
+#define PI(e) s_int[(e) * THREADS + l]
+  int q = 0;  // parity of the job
+  for (;;) {
+    pipe::bar_sync(1 + w, 64);
+    if (s_exit[w]) return;
+    double BL[N][N], BR[N][N], R12[N][N], RY[N][N], v0[N], gg[N], p[N], pinv[N], m_p[N][D], m_ext_p[N][D];
+    {
+      double jb[MB::JOB];
+#pragma unroll
+      for (int e = 0; e < MB::JOB / 2; ++e) {
+        const double2 v = reinterpret_cast<const double2*>(s_job)[e * THREADS + l];
+        jb[2 * e] = v.x;
+        jb[2 * e + 1] = v.y;
+      }
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        v0[i] = jb[MB::O_V0 + i];
+        gg[i] = jb[MB::O_G + i];
+        p[i] = jb[MB::O_P + i];
+        pinv[i] = jb[MB::O_PINV + i];
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          m_p[i][c] = jb[MB::O_MP + i * D + c];
+          m_ext_p[i][c] = jb[MB::O_MEP + i * D + c];
+        }
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          BL[i][j] = jb[MB::O_BL + i * N + j];
+          RY[i][j] = (j >= i) ? jb[MB::O_RY + Lay::tri(j, i)] : 0.0;
+          BR[i][j] = (i <= j) ? jb[MB::O_LP + Lay::tri(j, i)] : 0.0;  // L_p^T (upper)
+        }
+      }
+    }
+    const int reset = PI(0);
+    pipe::bar_arrive(1 + THREADS / 32 + w, 64);  // mailbox free
+    if (reset) {
+#pragma unroll
+      for (int e = 0; e < Lay::BW; ++e) PBW(e) = 0.0;
+#pragma unroll
+      for (int i = 0; i < N; ++i) PBW(OFF_G + i * N + i) = 1.0;
+    }
+    // right block of the predict QR
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+#pragma unroll
+      for (int c = 0; c < N; ++c) {
+        double wv = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          if (j == 0 && i > c) continue;  // still structurally zero
+          wv = fma(BL[i][j], BR[i][c], wv);
+        }
+        const double f = wv * gg[j];
+        R12[j][c] = fma(-f, v0[j], 0.0);
+#pragma unroll
+        for (int i = 0; i < N; ++i) BR[i][c] = fma(-f, BL[i][j], BR[i][c]);
+      }
+    }
+    double X[N][N];
+#pragma unroll
+    for (int i = N - 1; i >= 0; --i) {
+      const double inv = rcp(RY[i][i]);
+#pragma unroll
+      for (int c = 0; c < N; ++c) {
+        double acc = R12[i][c];
+#pragma unroll
+        for (int k = i + 1; k < N; ++k) acc = fma(-RY[i][k], X[k][c], acc);
+        X[i][c] = acc * inv;
+      }
+    }
+    double Gn[N][N], gn[N][D], Ln[N][N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        double acc = m_p[i][c];
+#pragma unroll
+        for (int k = 0; k < N; ++k) acc = fma(-X[k][i], m_ext_p[k][c], acc);
+        gn[i][c] = p[i] * acc;
+      }
+#pragma unroll
+      for (int j = 0; j < N; ++j) Gn[i][j] = (p[i] * X[j][i]) * pinv[j];
+#pragma unroll
+      for (int j = 0; j < N; ++j) Ln[i][j] = p[i] * BR[j][i];
+    }
+    // merge with the running conditional (A.4)
+    double Gm[N][N], gm[N][D], Lm[N][N];
+    {
+      double G1[N][N];
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) G1[i][j] = PBW(OFF_G + i * N + j);
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          double acc = G1[i][0] * Gn[0][j];
+#pragma unroll
+          for (int k = 1; k < N; ++k) acc = fma(G1[i][k], Gn[k][j], acc);
+          Gm[i][j] = acc;
+        }
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          double acc = PBW(OFF_g + i * D + c);
+#pragma unroll
+          for (int k = 0; k < N; ++k) acc = fma(G1[i][k], gn[k][c], acc);
+          gm[i][c] = acc;
+        }
+      }
+      double Mt[N][N], Mb[N][N];
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          double acc = G1[i][0] * Ln[0][j];
+#pragma unroll
+          for (int k = 1; k < N; ++k) acc = fma(G1[i][k], Ln[k][j], acc);
+          Mt[j][i] = acc;
+        }
+#pragma unroll
+      for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int i = 0; i < N; ++i) Mb[i][j] = (i <= j) ? PBW(OFF_LAM + Lay::tri(j, i)) : 0.0;
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        double sigma2 = 0.0;
+#pragma unroll
+        for (int i = j + 1; i < N; ++i) sigma2 = fma(Mt[i][j], Mt[i][j], sigma2);
+#pragma unroll
+        for (int i = 0; i <= j; ++i) sigma2 = fma(Mb[i][j], Mb[i][j], sigma2);
+        const Reflector rf = make_reflector(Mt[j][j], sigma2);
+#pragma unroll
+        for (int c = j + 1; c < N; ++c) {
+          double wv = 0.0;
+#pragma unroll
+          for (int i = j + 1; i < N; ++i) wv = fma(Mt[i][j], Mt[i][c], wv);
+#pragma unroll
+          for (int i = 0; i <= j; ++i) wv = fma(Mb[i][j], Mb[i][c], wv);
+          wv = fma(rf.v0, Mt[j][c], wv);
+          const double f = wv * rf.g;
+          Mt[j][c] = fma(-f, rf.v0, Mt[j][c]);
+#pragma unroll
+          for (int i = j + 1; i < N; ++i) Mt[i][c] = fma(-f, Mt[i][j], Mt[i][c]);
+#pragma unroll
+          for (int i = 0; i <= j; ++i) Mb[i][c] = fma(-f, Mb[i][j], Mb[i][c]);
+        }
+        Mt[j][j] = rf.beta;
+      }
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) Lm[i][j] = (j <= i) ? Mt[j][i] : 0.0;
+    }
+    // what the filter lane's bookkeeping decided (per lane: may diverge)
+    const int nops = PI(MB::i_nops(q));
+    for (int o = 0; o < nops; ++o) {
+      {
+        const int op = PI(MB::i_nops(q) + 1 + o);
+        double* d_ = (double*)__double_as_longlong(PJ(MB::O_DST + q * MAX_OPS + o));
+        if (op == pipe::OP_COMMIT) {
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+#pragma unroll
+            for (int j = 0; j < N; ++j) PBW(OFF_G + i * N + j) = Gm[i][j];
+#pragma unroll
+            for (int c = 0; c < D; ++c) PBW(OFF_g + i * D + c) = gm[i][c];
+#pragma unroll
+            for (int j = 0; j <= i; ++j) PBW(OFF_LAM + Lay::tri(i, j)) = Lm[i][j];
+          }
+        } else if (op == pipe::OP_RESET) {
+#pragma unroll
+          for (int e = 0; e < Lay::BW; ++e) PBW(e) = 0.0;
+#pragma unroll
+          for (int i = 0; i < N; ++i) PBW(OFF_G + i * N + i) = 1.0;
+        } else if (op == pipe::OP_STORE_MERGED) {
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+#pragma unroll
+            for (int j = 0; j < N; ++j) d_[OFF_G + i * N + j] = Gm[i][j];
+#pragma unroll
+            for (int c = 0; c < D; ++c) d_[OFF_g + i * D + c] = gm[i][c];
+#pragma unroll
+            for (int j = 0; j <= i; ++j) d_[OFF_LAM + Lay::tri(i, j)] = Lm[i][j];
+          }
+        } else if (op == pipe::OP_STORE_RUNNING) {
+#pragma unroll
+          for (int e = 0; e < Lay::BW; ++e) d_[e] = PBW(e);
+        } else if (op == pipe::OP_STORE_IDENTITY) {
+#pragma unroll
+          for (int e = 0; e < Lay::BW; ++e) d_[e] = 0.0;
+#pragma unroll
+          for (int i = 0; i < N; ++i) d_[OFF_G + i * N + i] = 1.0;
+        }
+      }
+    }
+    __syncwarp();
+    q ^= 1;
+  }
+#undef PBW
+#undef PJ
+#undef PI
+}
+}  // namespace pair
+
 #ifndef PN_MINBLOCKS
 #define PN_MINBLOCKS 2
 #endif
@@ -619,8 +863,9 @@ __device__ __noinline__ void backward_warp(Mail<N>& M, const int nmain) {
 //           same factor arithmetic as a thread-per-IVP lane; the n x d mean arrays live in global
 //           memory (L2 resident) and each thread owns the columns c = tid, tid + THREADS, ...;
 //           norms are reduced over the CTA.  Prob::D is a dummy (1) in this mode.
-template <class Prob, int NU, int STRAT, int GROUP, int BDIAG, int THREADS, int WIDE = 0, int SLICE = 0, int PIPE = 0>
-__global__ void __launch_bounds__(THREADS + 64 * PIPE, PIPE ? 1 : PN_MINBLOCKS) pn_scalar_kernel(const __grid_constant__ SolveArgs a) {
+template <class Prob, int NU, int STRAT, int GROUP, int BDIAG, int THREADS, int WIDE = 0, int SLICE = 0, int PIPE = 0, int PAIR = 0>
+__global__ void __launch_bounds__(THREADS * (1 + PAIR) + 64 * PIPE, (PIPE || PAIR) ? 1 : PN_MINBLOCKS)
+    pn_scalar_kernel(const __grid_constant__ SolveArgs a) {
   constexpr int N = NU + 1, DT = Prob::D, D = (GROUP > 1) ? 1 : DT, Q = Prob::Q, P = (Prob::P > 0 ? Prob::P : 1);
   constexpr int DV = (GROUP > 1) ? DT : 1;  // lanes ("virtual members") per IVP that own state
   static_assert(GROUP == 1 || (GROUP >= DT && (GROUP & (GROUP - 1)) == 0 && GROUP <= 32), "bad GROUP");
@@ -656,7 +901,7 @@ __global__ void __launch_bounds__(THREADS + 64 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
   double pipe_ck_t = 0.0;
   auto ck_cached = [&](long long k) -> double {
     const long long kc = k < a.K ? k : a.K - 1;
-    if constexpr (PIPE) {
+    if constexpr (PIPE || PAIR) {
       if (kc != pipe_ck_k) {
         pipe_ck_k = kc;
         pipe_ck_t = a.save_at[kc];
@@ -668,18 +913,37 @@ __global__ void __launch_bounds__(THREADS + 64 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
   };
 #ifdef PN_PIPE_STATS
   long long pipe_tm = clock64();
-#define PN_MAIN_PHASE(w) do { if (PIPE && tid == 0) { const long long now_ = clock64(); atomicAdd(a.ticket + (w), (unsigned long long)(now_ - pipe_tm)); pipe_tm = now_; } } while (0)
+#define PN_MAIN_PHASE(w) do { if ((PIPE || PAIR) && tid == 0 && blockIdx.x == 0) { const long long now_ = clock64(); atomicAdd(a.ticket + (w), (unsigned long long)(now_ - pipe_tm)); pipe_tm = now_; } } while (0)
 #else
 #define PN_MAIN_PHASE(w) do { } while (0)
 #endif
   // PIPE: preconditioner of the step the controller proposes, computed one iteration ahead (off the head of the chain)
   double pipe_spec_dt = __longlong_as_double(0x7ff8000000000000LL), pipe_spec_p[N], pipe_spec_pinv[N];
 
+  int* pair_exit = nullptr;
   extern __shared__ double smem[];
   // [element][thread]
   double* s_bw = smem;                                       // BW * THREADS (fixed-point only)
   double* s_pend = smem + (FIX ? Lay::BW : 0) * THREADS;     // PEND * THREADS
   double* s_state = s_pend + Lay::PEND * THREADS;            // MARG * THREADS: hidden state (mean, factor)
+  // PAIR: per-lane mailbox filter lane -> backward lane behind the state ([element][lane]); the running
+  // conditional in s_bw belongs to the backward lanes
+  static_assert(!PAIR || (GROUP == 1 && !WIDE && STRAT == 1 && !SLICE && !PIPE), "PAIR: thread-per-IVP fixed-point kernels");
+  using PMB = pair::Mailbox<N, D>;
+  double* s_job = s_state + Lay::MARG * THREADS;
+  int* s_int = (int*)(s_job + PMB::DOUBLES * THREADS);
+  if constexpr (PAIR) {
+    __shared__ int s_pair_exit[THREADS / 32];
+    if (threadIdx.x < THREADS / 32) s_pair_exit[threadIdx.x] = 0;
+    __syncthreads();
+    if (threadIdx.x >= THREADS) {
+      pair::backward_lanes<N, D, THREADS>(s_bw, s_job, s_int, s_pair_exit);
+      return;
+    }
+    pair_exit = s_pair_exit;
+  }
+  bool pair_started = false, pair_reset = false;
+  int pair_nops = 0, pair_q = 1;
   const int tid = threadIdx.x;
 #define SBW(e) s_bw[(e) * THREADS + tid]
 #define SPEND(e) s_pend[(e) * THREADS + tid]
@@ -763,6 +1027,11 @@ __global__ void __launch_bounds__(THREADS + 64 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
   };
 
   for (;;) {
+    if constexpr (PAIR) {
+      // the job and the op list of the previous iteration are complete: hand them to the backward lanes
+      __syncwarp();  // (lanes without a member come here early)
+      if (pair_started) pipe::bar_arrive(1 + (tid >> 5), 64);
+    }
     // ---- fetch a member ----------------------------------------------------------------
     // SLICE: a lane that has just lost its member looks for the next one at once; after an unsuccessful
     // look it only polls every eighth iteration (a poll is an L2 round trip that stalls the whole warp)
@@ -880,12 +1149,13 @@ __global__ void __launch_bounds__(THREADS + 64 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
         for (int i = 0; i < N; ++i)
 #pragma unroll
           for (int j = 0; j <= i; ++j) SL(i, j) = 0.0;
-        if (FIX) {
+        if (FIX && !PAIR) {
 #pragma unroll
           for (int e = 0; e < Lay::BW; ++e) SBW(e) = 0.0;
 #pragma unroll
           for (int i = 0; i < N; ++i) SBW(OFF_G + i * N + i) = 1.0;
         }
+        pair_reset = true;  // PAIR: the backward lane resets its running conditional in front of the next job
         t = a.save_at[0];
         dt_next = a.dt0;
         le_prev = 0.0;
@@ -949,6 +1219,18 @@ __global__ void __launch_bounds__(THREADS + 64 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
     }
     // warp-level vote keeps the loop convergent; the lane counts feed the utilisation statistics
     const unsigned active = __ballot_sync(0xffffffffu, have);
+    if constexpr (PAIR) {
+      if (active == 0u) {
+        // the backward lanes must have taken the last job out of the mailbox (and passed their exit check)
+        // before the exit flag goes up
+        if (pair_started) pipe::bar_sync(1 + THREADS / 32 + (tid >> 5), 64);
+        if ((tid & 31) == 0) pair_exit[tid >> 5] = 1;
+        __syncwarp();
+        pipe::bar_arrive(1 + (tid >> 5), 64);
+      }
+      pair_q ^= 1;  // (0 for the first job)
+      pair_nops = 0;
+    }
     if (active == 0u) {
       if constexpr (PIPE) {  // (have is uniform over the CTA in this mode: every main warp leaves here)
         if (tid == 0) pipe::mail<N>().exit_ = 1;
@@ -962,6 +1244,9 @@ __global__ void __launch_bounds__(THREADS + 64 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
     }
     stat_warp_iters += 1;
     PN_MAIN_PHASE(14);  // end of the previous iteration's tail / member fetch
+#ifdef PN_PIPE_STATS
+    if (PAIR && tid == 0 && blockIdx.x == 0) atomicAdd(a.ticket + 11, 1ULL);
+#endif
     if constexpr (SLICE) {
       // belt and braces: every warp re-derives the queue mask from the counters once in a while, so a
       // parked member could not stay invisible even if no warp ever ran completely out of work
@@ -970,7 +1255,11 @@ __global__ void __launch_bounds__(THREADS + 64 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
     }
     stat_lane_iters += __popc(active);
     stat_interp_iters += __popc(__ballot_sync(0xffffffffu, have && mode != MODE_STEP));
-    if (!have) continue;  // idle lane
+    if constexpr (!PAIR) {
+      if (!have) continue;  // idle lane
+    }
+    // (PAIR: idle lanes walk through the step on whatever their registers hold -- the named barriers inside it
+    // need the whole warp -- and leave in front of the bookkeeping)
 
     // ---- choose this iteration's prediction --------------------------------------------
     double t_ck = ck_cached(k_next);
@@ -1063,6 +1352,7 @@ __global__ void __launch_bounds__(THREADS + 64 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
         for (int k = 0; k < Q; ++k) h[k] = -J[k];
       }
     }
+    if constexpr (PAIR) PN_MAIN_PHASE(15);  // precondition + predicted mean + vector field
     // wide mode, pass 1: per owned column predict the mean, stage u = m_ext[0] for the stencil,
     // form the residual z (kept in shared memory) and the CTA-wide sum of squares
     double wide_zz = 0.0;
@@ -1173,7 +1463,7 @@ __global__ void __launch_bounds__(THREADS + 64 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
       double RY[N][N];   // upper
       double R12[N][N];  // full (fixed-point)
       double BR[N][N];   // bottom-right block, starts as L_p^T (upper), fills in (fixed-point)
-      if (FIX && !PIPE) {
+      if (FIX && !PIPE && !PAIR) {
 #pragma unroll
         for (int i = 0; i < N; ++i)
 #pragma unroll
@@ -1188,7 +1478,7 @@ __global__ void __launch_bounds__(THREADS + 64 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
         const double alpha = sigma * LQ[j * N + j];
         Reflector rf = make_reflector(alpha, sigma2);
         RY[j][j] = rf.beta;
-        if constexpr (PIPE) {
+        if constexpr (PIPE || PAIR) {
           pipe_v0[j] = rf.v0;
           pipe_g[j] = rf.g;
         }
@@ -1205,7 +1495,7 @@ __global__ void __launch_bounds__(THREADS + 64 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
 #pragma unroll
           for (int i = 0; i < N; ++i) BL[i][c] = fma(-f, BL[i][j], BL[i][c]);
         }
-        if (FIX && !PIPE) {
+        if (FIX && !PIPE && !PAIR) {
           // right block columns: top entry starts at 0
 #pragma unroll
           for (int c = 0; c < N; ++c) {
@@ -1248,7 +1538,45 @@ __global__ void __launch_bounds__(THREADS + 64 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
           M.stats = a.ticket;
         }
       }
-      if (FIX && !PIPE) {
+      if constexpr (PAIR) {
+        // the backward lanes took the previous job out of the mailbox long ago (they arrive at this barrier as
+        // soon as they have loaded it): no waiting here in the steady state
+        if (pair_started) pipe::bar_sync(1 + THREADS / 32 + (tid >> 5), 64);
+        pair_started = true;
+        // (the backward lane has loaded the previous job, so it is done with the op list of the job before that,
+        // which is the buffer this iteration writes: no ops until the bookkeeping says otherwise)
+        s_int[PMB::i_nops(pair_q) * THREADS + tid] = 0;
+        // the lane's mailbox: reflectors of the predict QR, R factor, L_p, preconditioner, predicted means
+        {
+          double jb[PMB::JOB];
+          jb[PMB::JOB - 1] = 0.0;  // (padding of an odd job)
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+            jb[PMB::O_V0 + i] = pipe_v0[i];
+            jb[PMB::O_G + i] = pipe_g[i];
+            jb[PMB::O_P + i] = p[i];
+            jb[PMB::O_PINV + i] = pinv[i];
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+              jb[PMB::O_MP + i * D + c] = m_p[i][c];
+              jb[PMB::O_MEP + i * D + c] = m_ext_p[i][c];
+            }
+#pragma unroll
+            for (int j = 0; j < N; ++j) jb[PMB::O_BL + i * N + j] = BL[i][j];
+#pragma unroll
+            for (int j = i; j < N; ++j) jb[PMB::O_RY + Lay::tri(j, i)] = RY[i][j];
+#pragma unroll
+            for (int j = 0; j <= i; ++j) jb[PMB::O_LP + Lay::tri(i, j)] = L_p[i][j];
+          }
+#pragma unroll
+          for (int e = 0; e < PMB::JOB / 2; ++e)
+            reinterpret_cast<double2*>(s_job)[e * THREADS + tid] = make_double2(jb[2 * e], jb[2 * e + 1]);
+        }
+        s_int[0 * THREADS + tid] = pair_reset ? 1 : 0;
+        pair_reset = false;
+        PN_MAIN_PHASE(16);  // calibration + left block of the predict QR + mailbox
+      }
+      if (FIX && !PIPE && !PAIR) {
         // The lower-right block BR is NOT triangularised: BR^T is already a valid square-root factor
         // of the backward noise (BR^T BR = R_XY^T R_XY) and the merge below re-triangularises anyway.
         // That removes n-1 serial Householder chains per step.
@@ -1294,7 +1622,7 @@ __global__ void __launch_bounds__(THREADS + 64 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
     // merge with the running conditional (A.4); running conditional lives in shared memory
     double Gm[N][N], gm[N][D], Lm[N][N];
     auto merge_running_conditional = [&]() {
-    if (FIX && !PIPE) {
+    if (FIX && !PIPE && !PAIR) {
       double G1[N][N];
 #pragma unroll
       for (int i = 0; i < N; ++i)
@@ -1480,6 +1808,7 @@ __global__ void __launch_bounds__(THREADS + 64 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
     if constexpr (PIPE) {
       if (pipe_F) corrected_factor();
     }
+    if constexpr (PAIR) PN_MAIN_PHASE(17);  // correction + error norm
     // PI controller
     double fac, le_now;
     {
@@ -1496,6 +1825,7 @@ __global__ void __launch_bounds__(THREADS + 64 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
       corrected_factor();
       merge_running_conditional();
     }
+    if constexpr (PAIR) PN_MAIN_PHASE(18);  // controller + corrected factor
     if constexpr (PIPE) {
       pipe_spec_dt = fac * dt;  // = dt_next of an attempted step (the bookkeeping below forms the same product)
       precondition(pipe_spec_dt, pipe_spec_p, pipe_spec_pinv);
@@ -1505,6 +1835,9 @@ __global__ void __launch_bounds__(THREADS + 64 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
     // PIPE: the backward warp has published X by now (it is busy with the merge); the running G the offset
     // update needs is the buffer it is NOT writing.  Everything the bookkeeping below wants done to the
     // running conditional is queued as an op and handed over in one piece (BAR_ACT).
+    if constexpr (PAIR) {
+      if (!have) continue;  // idle lane (its mailbox carries no ops)
+    }
     const double* pipe_G1 = nullptr;  // PIPE: the running G (before this step's merge) and X, in shared memory
     const double* pipe_X = nullptr;
     if constexpr (PIPE) {
@@ -1526,6 +1859,14 @@ __global__ void __launch_bounds__(THREADS + 64 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
       PN_MAIN_PHASE(20);  // X wait + load
     }
     auto pipe_op = [&](int code, double* dst) {
+      if constexpr (PAIR) {
+        if (pair_nops < pair::MAX_OPS) {
+          s_int[(PMB::i_nops(pair_q) + 1 + pair_nops) * THREADS + tid] = code;
+          s_job[(PMB::O_DST + pair_q * pair::MAX_OPS + pair_nops) * THREADS + tid] = __longlong_as_double((long long)dst);
+          pair_nops += 1;
+          s_int[PMB::i_nops(pair_q) * THREADS + tid] = pair_nops;
+        }
+      }
       if constexpr (PIPE) {
         if (tid == 0 && pipe_nops < pipe::MAX_OPS) {
           pipe::Mail<N>& M = pipe::mail<N>();
@@ -1660,6 +2001,10 @@ __global__ void __launch_bounds__(THREADS + 64 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
 
     auto store_cond = [&](double* dst /* element stride VB */) {
       if (!real) return;
+      if constexpr (PAIR) {
+        pipe_op(pipe::OP_STORE_MERGED, dst);
+        return;
+      }
 #pragma unroll
       for (int i = 0; i < N; ++i) {
 #pragma unroll
@@ -1672,13 +2017,17 @@ __global__ void __launch_bounds__(THREADS + 64 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
     };
     auto store_identity_cond = [&](double* dst) {
       if (!real) return;
+      if constexpr (PAIR) {
+        pipe_op(pipe::OP_STORE_IDENTITY, dst);
+        return;
+      }
 #pragma unroll
       for (int e = 0; e < Lay::BW; ++e) dst[e] = 0.0;
 #pragma unroll
       for (int i = 0; i < N; ++i) dst[OFF_G + i * N + i] = 1.0;
     };
     auto bw_commit = [&]() {  // running conditional <- merged result
-      if constexpr (PIPE) {
+      if constexpr (PIPE || PAIR) {
         pipe_op(pipe::OP_COMMIT, nullptr);
         return;
       }
@@ -1693,7 +2042,7 @@ __global__ void __launch_bounds__(THREADS + 64 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
       }
     };
     auto bw_reset = [&]() {  // running conditional <- identity (A.2)
-      if constexpr (PIPE) {
+      if constexpr (PIPE || PAIR) {
         pipe_op(pipe::OP_RESET, nullptr);
         return;
       }
@@ -1762,7 +2111,9 @@ __global__ void __launch_bounds__(THREADS + 64 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
           }
         }
         if (FIX) {
-          if (real) {
+          if constexpr (PAIR) {
+            pipe_op(pipe::OP_STORE_RUNNING, slot);
+          } else if (real) {
 #pragma unroll
             for (int e = 0; e < Lay::BW; ++e) slot[e] = SBW(e);
           }
@@ -1924,6 +2275,7 @@ __global__ void __launch_bounds__(THREADS + 64 * PIPE, PIPE ? 1 : PN_MINBLOCKS) 
       k_next += 1;
       after_checkpoint(finished);
     }
+    if constexpr (PAIR) PN_MAIN_PHASE(19);  // bookkeeping
     if constexpr (PIPE) {
       if (tid == 0) pipe::mail<N>().nops = (pipe_nops < pipe::MAX_OPS) ? pipe_nops : pipe::MAX_OPS;
       pipe::bar_arrive(pipe::BAR_ACT, THREADS + 32);

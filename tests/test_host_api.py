@@ -60,7 +60,12 @@ def test_supported_and_workspace_queries_need_no_gpu(monkeypatch):
     header2 = (256 + 2 * 128 * 4 + B2 * 8 + 255) // 256 * 256
     queues = ((K2 - 1) * B2 * 4 + 255) // 256 * 256
     ctx = ((n * n + n * D + n * (n + 1) // 2) + (n * D + n * (n + 1) // 2) + 8 + 1) // 2 * 2
+    # (ensembles of up to 148 x 128 members are served by the filter-lane + backward-lane build, which runs every
+    # member to completion: no scheduler region)
+    assert _cabi.workspace_bytes(_desc(_cabi, batch=B2, num_save_at=K2)) == header2 + K2 * slot * B2 * 8
+    monkeypatch.setenv("PN_B200_PAIR", "0")
     assert _cabi.workspace_bytes(_desc(_cabi, batch=B2, num_save_at=K2)) == header2 + K2 * slot * B2 * 8 + queues + 1024 + B2 * ctx * 8
+    monkeypatch.delenv("PN_B200_PAIR")
     # ... but not for the filter strategy, trajectory recording or fixed grids
     slot_f = n * D + n * (n + 1) // 2
     assert _cabi.workspace_bytes(_desc(_cabi, batch=B2, num_save_at=K2, strategy=0)) == header2 + K2 * slot_f * B2 * 8
