@@ -32,10 +32,11 @@ template <int N, int DD>
 struct DenseRowsLayout {
   static constexpr int Dn = N * DD;
   static constexpr int MAT = Dn * Dn;
-  static constexpr int VB = 2 * Dn + 2;  // one reflector broadcast buffer
+  static constexpr int VB = 2 * Dn + 2;  // one reflector broadcast buffer (even: it is read and written as 16-byte pairs)
   static constexpr int TABLES = 2 * N * N;  // L_Q and the flipped Pascal matrix, once per CTA
-  // shared memory per IVP slot (doubles): 7 matrices + vectors, see the take() list in the kernel
-  static constexpr int SMEM_SLOT = 7 * MAT + 9 * Dn + 2 * DD * Dn + DD * DD + 2 * VB;
+  // shared memory per IVP slot (doubles): 7 matrices + vectors, see the take() list in the kernel; rounded up to an
+  // even count so that the broadcast buffers at the front of every slot stay 16-byte aligned
+  static constexpr int SMEM_SLOT = (7 * MAT + 9 * Dn + 2 * DD * Dn + DD * DD + 2 * VB + 1) & ~1;
 };
 
 template <class Prob, int NU, int STRAT, int LANES, int WARPS>
@@ -77,6 +78,7 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_rows_kernel(const __grid_
 
   double* sp = smem + RL::TABLES + (size_t)(warp * GPW + sub) * RL::SMEM_SLOT;
   auto take = [&](int count) { double* r = sp; sp += count; return r; };
+  double* vb = take(2 * VB);  // first: 16-byte aligned (reflector broadcasts move as double2)
   // state
   double* S_m = take(Dn);   double* S_L = take(MAT);
   double* S_G = take(MAT);  double* S_g = take(Dn);  double* S_Lam = take(MAT);
@@ -96,13 +98,33 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_rows_kernel(const __grid_
   double* gn_s = take(Dn);  double* dinv = take(Dn);
   double* H = take(d * Dn); double* HLs = take(d * Dn);
   double* Rs = take(d * d);
-  double* vb = take(2 * VB);
 
   double a1row[N];  // row ci of the flipped Pascal matrix
 #pragma unroll
   for (int j = 0; j < N; ++j) a1row[j] = A1s[ci * N + j];
   const double inv_sqrt_d = rcp(dsqrt((double)d));
 
+  // Reflector broadcast as 16-byte pairs: lane `owner` stores the pairs that cover elements [e0, e1) of `src`
+  // (a register array indexed like the buffer), every lane reads them back into `dst`.  Elements outside [e0, e1)
+  // that share a pair are stored / loaded as well and simply not used.
+  auto publish_pairs = [&](double* buf, bool owner, const double* src, int e0, int e1) {
+    if (owner) {
+      double2* b2 = reinterpret_cast<double2*>(buf);
+#pragma unroll
+      for (int pp = 0; pp < VB / 2; ++pp)
+        if (pp >= (e0 >> 1) && pp <= ((e1 - 1) >> 1)) b2[pp] = make_double2(src[2 * pp], src[2 * pp + 1]);
+    }
+  };
+  auto fetch_pairs = [&](const double* buf, double* dst, int e0, int e1) {
+    const double2* b2 = reinterpret_cast<const double2*>(buf);
+#pragma unroll
+    for (int pp = 0; pp < VB / 2; ++pp)
+      if (pp >= (e0 >> 1) && pp <= ((e1 - 1) >> 1)) {
+        const double2 t = b2[pp];
+        dst[2 * pp] = t.x;
+        dst[2 * pp + 1] = t.y;
+      }
+  };
   auto gsync = [&]() { __syncwarp(gmask); };
   auto gcopy = [&](double* dst, const double* src, int count) {
     for (int e = c; e < count; e += LANES) dst[e] = src[e];
@@ -128,19 +150,16 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_rows_kernel(const __grid_
 #pragma unroll
     for (int j = 0; j < d; ++j) {
       double* vbj = vb + (j & 1) * VB;
-      if (c == j) {
+      double src[VB], v[VB];
 #pragma unroll
-        for (int i = j; i < LIM; ++i) vbj[i] = rm[i];
-      }
+      for (int i = 0; i < VB; ++i) src[i] = (i < LIM) ? rm[i] : 0.0;
+      publish_pairs(vbj, c == j, src, j, LIM);
       __syncwarp();
-      const double alpha = vbj[j];
-      double v[LIM];
+      fetch_pairs(vbj, v, j, LIM);
+      const double alpha = v[j];
       double sigma2 = 0.0;
 #pragma unroll
-      for (int i = j + 1; i < LIM; ++i) {
-        v[i] = vbj[i];
-        sigma2 = fma(v[i], v[i], sigma2);
-      }
+      for (int i = j + 1; i < LIM; ++i) sigma2 = fma(v[i], v[i], sigma2);
       const Reflector R = make_reflector(alpha, sigma2);
       double w = 0.0;
 #pragma unroll
@@ -355,20 +374,16 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_rows_kernel(const __grid_
         const int jq = j / d, jr = j - jq * d;
         const double top_l = sigma * ((cl == jr) ? LQs[ci * N + jq] : 0.0);
         double* vbj = vb + (j & 1) * VB;
-        if (c == j) {
+        double src[VB], v[VB];
 #pragma unroll
-          for (int k = 0; k < Dn; ++k) vbj[k] = lb[k];
-          vbj[Dn] = top_l;
-        }
+        for (int k = 0; k < VB; ++k) src[k] = (k < Dn) ? lb[k] : ((k == Dn) ? top_l : 0.0);
+        publish_pairs(vbj, c == j, src, 0, Dn + 1);
         __syncwarp();
-        double v[Dn];
+        fetch_pairs(vbj, v, 0, Dn + 1);
         double sigma2 = 0.0;
 #pragma unroll
-        for (int k = 0; k < Dn; ++k) {
-          v[k] = vbj[k];
-          sigma2 = fma(v[k], v[k], sigma2);
-        }
-        const Reflector R = make_reflector(vbj[Dn], sigma2);
+        for (int k = 0; k < Dn; ++k) sigma2 = fma(v[k], v[k], sigma2);
+        const Reflector R = make_reflector(v[Dn], sigma2);
         double wl = 0.0, wr = 0.0;
 #pragma unroll
         for (int k = 0; k < Dn; ++k) {
@@ -460,24 +475,23 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_rows_kernel(const __grid_
 #pragma unroll
         for (int j = 0; j < Dn; ++j) {
           double* vbj = vb + (j & 1) * VB;
-          if (c == j) {
+          double src[VB], rd[VB];
 #pragma unroll
-            for (int i = j; i < Dn; ++i) vbj[i] = tt[i];
-#pragma unroll
-            for (int k = 0; k <= j; ++k) vbj[Dn + k] = bl[k];
-          }
+          for (int e = 0; e < VB; ++e) src[e] = (e < Dn) ? tt[e] : ((e < 2 * Dn) ? bl[e - Dn] : 0.0);
+          publish_pairs(vbj, c == j, src, j, Dn + j + 1);
           __syncwarp();
-          const double alpha = vbj[j];
+          fetch_pairs(vbj, rd, j, Dn + j + 1);
+          const double alpha = rd[j];
           double vt[Dn], vl[Dn];
           double sigma2 = 0.0;
 #pragma unroll
           for (int i = j + 1; i < Dn; ++i) {
-            vt[i] = vbj[i];
+            vt[i] = rd[i];
             sigma2 = fma(vt[i], vt[i], sigma2);
           }
 #pragma unroll
           for (int k = 0; k <= j; ++k) {
-            vl[k] = vbj[Dn + k];
+            vl[k] = rd[Dn + k];
             sigma2 = fma(vl[k], vl[k], sigma2);
           }
           const Reflector R = make_reflector(alpha, sigma2);
@@ -556,19 +570,16 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_rows_kernel(const __grid_
 #pragma unroll
       for (int j = 0; j < LIM - 1; ++j) {
         double* vbj = vb + (j & 1) * VB;
-        if (c == j) {
+        double src[VB], v[VB];
 #pragma unroll
-          for (int i = j; i < LIM; ++i) vbj[i] = mc[i];
-        }
+        for (int i = 0; i < VB; ++i) src[i] = (i < LIM) ? mc[i] : 0.0;
+        publish_pairs(vbj, c == j, src, j, LIM);
         __syncwarp();
-        const double alpha = vbj[j];
-        double v[LIM];
+        fetch_pairs(vbj, v, j, LIM);
+        const double alpha = v[j];
         double sigma2 = 0.0;
 #pragma unroll
-        for (int i = j + 1; i < LIM; ++i) {
-          v[i] = vbj[i];
-          sigma2 = fma(v[i], v[i], sigma2);
-        }
+        for (int i = j + 1; i < LIM; ++i) sigma2 = fma(v[i], v[i], sigma2);
         const Reflector R = make_reflector(alpha, sigma2);
         double w = 0.0;
 #pragma unroll
