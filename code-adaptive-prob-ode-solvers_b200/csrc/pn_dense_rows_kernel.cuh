@@ -34,9 +34,12 @@ struct DenseRowsLayout {
   static constexpr int MAT = Dn * Dn;
   static constexpr int VB = 2 * Dn + 2;  // one reflector broadcast buffer (even: it is read and written as 16-byte pairs)
   static constexpr int TABLES = 2 * N * N;  // L_Q and the flipped Pascal matrix, once per CTA
-  // shared memory per IVP slot (doubles): 7 matrices + vectors, see the take() list in the kernel; rounded up to an
-  // even count so that the broadcast buffers at the front of every slot stay 16-byte aligned
-  static constexpr int SMEM_SLOT = (7 * MAT + 9 * Dn + 2 * DD * Dn + DD * DD + 2 * VB + 1) & ~1;
+  static constexpr int TRI = Dn * (Dn + 1) / 2;  // a packed lower-triangular factor (row i at i (i + 1) / 2)
+  // shared memory per IVP slot (doubles): 6 full matrices, the running Lam packed (it is only read as one row per
+  // lane by the merge and copied / emitted between steps: packing it is what lets an eighth warp fit on an SM at
+  // D = 15) + vectors, see the take() list in the kernel; rounded up to an even count so that the broadcast buffers
+  // at the front of every slot stay 16-byte aligned
+  static constexpr int SMEM_SLOT = (6 * MAT + TRI + 9 * Dn + 2 * DD * Dn + DD * DD + 2 * VB + 1) & ~1;
 };
 
 template <class Prob, int NU, int STRAT, int LANES, int WARPS>
@@ -81,7 +84,7 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_rows_kernel(const __grid_
   double* vb = take(2 * VB);  // first: 16-byte aligned (reflector broadcasts move as double2)
   // state
   double* S_m = take(Dn);   double* S_L = take(MAT);
-  double* S_G = take(MAT);  double* S_g = take(Dn);  double* S_Lam = take(MAT);
+  double* S_G = take(MAT);  double* S_g = take(Dn);  double* S_Lam = take(RL::TRI);  // (packed lower triangle)
   // step outputs.  (m_new, L_new) is only written by an attempted step (MODE_STEP), so it doubles
   // as the accepted-but-uncommitted state while the checkpoints inside that step are interpolated.
   double* m_ext = take(Dn); double* m_new = take(Dn);
@@ -103,6 +106,7 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_rows_kernel(const __grid_
 #pragma unroll
   for (int j = 0; j < N; ++j) a1row[j] = A1s[ci * N + j];
   const double inv_sqrt_d = rcp(dsqrt((double)d));
+  const int tri_cr = cr * (cr + 1) / 2;  // row cr of a packed lower-triangular factor
 
   // Reflector broadcast as 16-byte pairs: lane `owner` stores the pairs that cover elements [e0, e1) of `src`
   // (a register array indexed like the buffer), every lane reads them back into `dst`.  Elements outside [e0, e1)
@@ -130,12 +134,21 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_rows_kernel(const __grid_
     for (int e = c; e < count; e += LANES) dst[e] = src[e];
     __syncwarp(gmask);
   };
+  // running Lam <- merged Lam of this step (W2, full rows): every lane packs its own row
+  auto pack_lam = [&]() {
+    if (act) {
+#pragma unroll
+      for (int k = 0; k < Dn; ++k)
+        if (k <= c) S_Lam[tri_cr + k] = W2[c * Dn + k];
+    }
+    __syncwarp(gmask);
+  };
   auto set_identity = [&]() {
     for (int e = c; e < MAT; e += LANES) {
       const int i = e / Dn, j = e - i * Dn;
       S_G[e] = (i == j) ? 1.0 : 0.0;
-      S_Lam[e] = 0.0;
     }
+    for (int e = c; e < RL::TRI; e += LANES) S_Lam[e] = 0.0;
     for (int e = c; e < Dn; e += LANES) S_g[e] = 0.0;
     __syncwarp(gmask);
   };
@@ -470,7 +483,7 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_rows_kernel(const __grid_
           }
         }
 #pragma unroll
-        for (int k = 0; k < Dn; ++k) bl[k] = S_Lam[cr * Dn + k];
+        for (int k = 0; k < Dn; ++k) bl[k] = (k <= cr) ? S_Lam[tri_cr + k] : 0.0;
         // QR of [T^T ; Lam_run^T]: top block full, bottom block upper triangular
 #pragma unroll
         for (int j = 0; j < Dn; ++j) {
@@ -628,6 +641,14 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_rows_kernel(const __grid_
       }
       for (int e = c; e < Dn; e += LANES) dst[MAT + e] = g_[e];
     };
+    auto emit_running_cond = [&](double* dst) {  // (S_G, S_g, S_Lam): Lam is packed
+      for (int e = c; e < MAT; e += LANES) {
+        const int i = e / Dn, j = e - i * Dn;
+        dst[e] = S_G[e];
+        dst[MAT + Dn + e] = (j <= i) ? S_Lam[i * (i + 1) / 2 + j] : 0.0;
+      }
+      for (int e = c; e < Dn; e += LANES) dst[MAT + e] = S_g[e];
+    };
     auto emit_identity_cond = [&](double* dst) {
       for (int e = c; e < MAT; e += LANES) {
         dst[e] = ((e / Dn) == (e % Dn)) ? 1.0 : 0.0;
@@ -643,7 +664,7 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_rows_kernel(const __grid_
       while (k_next < a.K && !(t + TIME_EPS < a.save_at[k_next])) {
         double* slot = slot_base + (size_t)k_next * SLOT;
         if (FIX) {
-          emit_cond(slot, S_G, S_g, S_Lam);
+          emit_running_cond(slot);
           if (k_next == a.K - 1) {
             emit_identity_cond(slot_base);
             emit_marg(slot_base + Lay::BW, S_m, S_L);
@@ -670,7 +691,7 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_rows_kernel(const __grid_
         if (FIX) {
           gcopy(S_G, Gm, MAT);
           gcopy(S_g, gm, Dn);
-          gcopy(S_Lam, Lm, MAT);
+          pack_lam();
         }
         mode = MODE_STEP;
         resolve_hits();
@@ -701,7 +722,7 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_rows_kernel(const __grid_
             if (FIX) {
               gcopy(S_G, Gm, MAT);
               gcopy(S_g, gm, Dn);
-              gcopy(S_Lam, Lm, MAT);
+              pack_lam();
             }
             resolve_hits();
           }

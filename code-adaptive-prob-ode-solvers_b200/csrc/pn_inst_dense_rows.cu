@@ -5,8 +5,8 @@ namespace pn {
 using Brusselator2r = Brusselator<2>;
 }  // namespace pn
 PN_REGISTER_DENSE_ROWS(RigidBody, 2, 1, 16, 1);
-PN_REGISTER_DENSE_ROWS(RigidBody, 4, 1, 16, 1);
-PN_REGISTER_DENSE_ROWS(RigidBody, 4, 0, 16, 1);
+PN_REGISTER_DENSE_ROWS(RigidBody, 4, 1, 16, 2);  // two warps per CTA: four CTAs = eight warps per SM at D = 15
+PN_REGISTER_DENSE_ROWS(RigidBody, 4, 0, 16, 2);
 PN_REGISTER_DENSE_ROWS(LotkaVolterra, 4, 1, 16, 1);
 PN_REGISTER_DENSE_ROWS(ThreeBody, 4, 1, 16, 1);
 PN_REGISTER_DENSE_ROWS(Brusselator2r, 4, 1, 32, 1);  // D = 20: one IVP per warp

@@ -185,7 +185,7 @@ struct DenseRowsInstance {
     KernelEntry e = DenseInstance<Prob, NU, STRAT, WARPS>::entry();  // same slots, same smoothing kernel
     e.family = FAMILY_DENSE_ROWS;
     e.group = LANES;
-    e.smem_doubles = (32 / LANES) * RL::SMEM_SLOT + RL::TABLES;  // per warp, see make_plan
+    e.smem_doubles = (32 / LANES) * RL::SMEM_SLOT + (RL::TABLES + WARPS - 1) / WARPS;  // per warp (the tables exist once per CTA), see make_plan
     e.solve_func = (const void*)&pn_dense_rows_kernel<Prob, NU, STRAT, LANES, WARPS>;
     e.launch_solve = &launch_solve;
     return e;
