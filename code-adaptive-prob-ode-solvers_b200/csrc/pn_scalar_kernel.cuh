@@ -643,7 +643,11 @@ __device__ __noinline__ void backward_lanes(double* s_bw, double* s_job, int* s_
   using Lay = Layout<N, D>;
   using MB = Mailbox<N, D>;
   constexpr int OFF_G = 0, OFF_g = N * N, OFF_LAM = N * N + N * D;
-  const int l = threadIdx.x - THREADS, w = l >> 5;
+  // backward warp pw serves filter warp (pw + NW / 2) mod NW: filter warp w issues from scheduler w mod 4, its
+  // backward lanes from the scheduler opposite, so that a lone pair (small ensembles) does not share one
+  constexpr int NW = THREADS / 32;
+  const int lraw = threadIdx.x - THREADS;
+  const int w = ((lraw >> 5) + NW / 2) % NW, l = w * 32 + (lraw & 31);
 #define PBW(e) s_bw[(e) * THREADS + l]
 #define PJ(e) s_job[(e) * THREADS + l]
 #define PI(e) s_int[(e) * THREADS + l]
