@@ -249,6 +249,30 @@ def ncu_dram_bytes():
     return (total, os.path.relpath(path, ROOT)) if seen == 2 else (None, None)
 
 
+def ncu_instruction_fetch():
+    """The second bound of the headline kernel, from the same committed ncu summary: its straight-line step (40 KB of
+    SASS) does not fit an SM's instruction cache, so every round of an SM's eight warps refetches it from the GPC-level
+    instruction cache (ncu unit `gcc`), whose request rate is what the launch saturates."""
+    cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_scalar_kernel*ncu.txt")))
+    cands = [c for c in cands if "_v1_" not in c]
+    if not cands:
+        return None
+    vals = {}
+    for line in open(cands[-1]):
+        t = line.split()
+        if len(t) >= 2 and t[0] in ("gcc__cache_requests_type_instruction.sum", "smsp__inst_executed.sum",
+                                    "gcc__cache_requests_type_instruction.sum.pct_of_peak_sustained_elapsed"):
+            vals[t[0]] = float(t[1])
+    if len(vals) != 3:
+        return None
+    req, inst = vals["gcc__cache_requests_type_instruction.sum"], vals["smsp__inst_executed.sum"]
+    return {
+        "bound": "instruction fetch (GPC-level instruction cache requests)", "frac": vals["gcc__cache_requests_type_instruction.sum.pct_of_peak_sustained_elapsed"] / 100.0,
+        "requests_per_launch": req, "warp_instructions_per_launch": inst, "lines_refetched_per_instruction_line": req * 8.0 / inst,
+        "source": f"gcc__cache_requests_type_instruction.sum(.pct_of_peak_sustained_elapsed), ncu --set full, {os.path.relpath(cands[-1], ROOT)}",
+    }  # fmt: skip
+
+
 def cpu_sample_size(members, cores):
     return int(min(members, max(512, 640 * cores)))  # ~10-20 s of CPU work on the VdP workload
 
@@ -544,6 +568,7 @@ def main():
                 "peak_source": "DFMA-chain microbenchmark in this run (pn_b200_measure_fp64_peak); MEASURED_PEAKS.json has no fp64 entry",
                 "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650"},
+                "instruction_fetch": ncu_instruction_fetch() if wl.name == "vdp" else None,
             },
             "clocks": head["clocks"],
         }  # fmt: skip

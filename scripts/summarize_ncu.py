@@ -54,6 +54,9 @@ KEYS = [
     "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+    # instruction fetch: requests of the SMs' instruction caches to the GPC-level cache (gcc) and what it forwards to L2
+    "gcc__cache_requests_type_instruction.sum", "gcc__cache_requests_type_instruction.sum.pct_of_peak_sustained_elapsed",
+    "gcc__average_cache_request_hit_rate.pct", "gcc__xbar2gcc_sectors.sum",
 ]
 
 
