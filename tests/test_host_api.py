@@ -167,3 +167,20 @@ def test_no_gpu_means_loud_failure_not_a_fallback():
     solve = ivpsolvers.solve("ts0-2", vf, u0[0], save_at=np.linspace(*tspan, num=5), dt0=0.1, atol=1e-3, rtol=1e-3)
     with pytest.raises(_cabi.SolverError):
         solve(u0, args)
+
+
+def test_bench_reads_its_roofline_side_inputs_from_the_committed_ncu_summary():
+    """bench.py takes the DRAM traffic and the instruction-fetch bound of the headline kernel from the newest
+    committed `ncu --set full` summary under profiles/ (no hard-coded constants): both must parse."""
+    import importlib.util
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("pn_bench_module", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    traffic, src = bench.ncu_dram_bytes()
+    assert traffic is not None and 1e8 < traffic < 1e11 and src.startswith("profiles")
+    fetch = bench.ncu_instruction_fetch()
+    assert fetch is not None and 0.5 < fetch["frac"] <= 1.0
+    assert 0.05 < fetch["lines_refetched_per_instruction_line"] < 0.5
