@@ -491,7 +491,7 @@ __device__ __noinline__ void backward_warp(Mail<N>& M, const int nmain) {
     double X[N][N];
 #pragma unroll
     for (int i = N - 1; i >= 0; --i) {
-      const double inv = rcp(RY[i][i]);
+      const double inv = rcp_raw(RY[i][i]);
 #pragma unroll
       for (int c = 0; c < N; ++c) {
         double acc = R12[i][c];
@@ -711,7 +711,7 @@ __device__ __noinline__ void backward_lanes(double* s_bw, double* s_job, int* s_
     double X[N][N];
 #pragma unroll
     for (int i = N - 1; i >= 0; --i) {
-      const double inv = rcp(RY[i][i]);
+      const double inv = rcp_raw(RY[i][i]);
 #pragma unroll
       for (int c = 0; c < N; ++c) {
         double acc = R12[i][c];
@@ -1284,8 +1284,11 @@ __global__ void __launch_bounds__(THREADS * (1 + PAIR) + 64 * PIPE, (PIPE || PAI
     double p[N], pinv[N];
     auto precondition = [&](double dt_, double (&p_)[N], double (&pinv_)[N]) {
       double adt = fabs(dt_);
-      double sq = dsqrt(adt);
-      double isq = rcp(sq), idt = rcp(adt);
+      // |dt| of a step that matters is a positive normal number (a step or an interpolation interval longer than
+      // TIME_EPS): the unguarded fast paths are exact; the 0 / inf selects of rcp() / dsqrt() were ~8 instructions
+      // per call of an instruction-fetch-bound step
+      double sq = dsqrt_raw(adt);
+      double isq = rcp_raw(sq), idt = rcp_raw(adt);
       double dtp = 1.0, idtp = 1.0;
 #pragma unroll
       for (int k = 0; k <= NU; ++k) {
@@ -1423,7 +1426,7 @@ __global__ void __launch_bounds__(THREADS * (1 + PAIR) + 64 * PIPE, (PIPE || PAI
         for (int i = j; i <= Q; ++i) acc = fma(h[i] * p[i], LQ[i * N + j], acc);
         s2 = fma(acc, acc, s2);
       }
-      double s = dsqrt(s2);
+      double s = dsqrt_raw(s2);  // s2 >= (p_q LQ_qq)^2 > 0
       double zz = 0.0;
       if constexpr (WIDE) {
         zz = wide_zz;
@@ -1435,7 +1438,7 @@ __global__ void __launch_bounds__(THREADS * (1 + PAIR) + 64 * PIPE, (PIPE || PAI
         if (!BDIAG) zz = group_sum<GROUP>(zz, gmask);
       }
       mle_zz = zz;
-      double sigma_hat = dsqrt(zz) * rcp(s);
+      double sigma_hat = dsqrt(zz) * rcp_raw(s);
       sigma_hat = BDIAG ? sigma_hat : sigma_hat * inv_sqrt_d;
       err = (fabs(dt) * sigma_hat) * s;
       sigma = (mode == MODE_STEP) ? ((a.calibration == 1) ? sigma_hat : sigma_given) : sigma_given;
@@ -1587,7 +1590,7 @@ __global__ void __launch_bounds__(THREADS * (1 + PAIR) + 64 * PIPE, (PIPE || PAI
         // X = RY^{-1} R12 (back substitution); G_p = X^T
 #pragma unroll
         for (int i = N - 1; i >= 0; --i) {
-          double inv = rcp(RY[i][i]);
+          double inv = rcp_raw(RY[i][i]);  // a zero pivot (sigma = 0 and L = 0) poisons X with NaN either way (0 * inf)
 #pragma unroll
           for (int c = 0; c < N; ++c) {
             double acc = R12[i][c];
@@ -1744,7 +1747,7 @@ __global__ void __launch_bounds__(THREADS * (1 + PAIR) + 64 * PIPE, (PIPE || PAI
         hL[j] = acc;
         S = fma(acc, acc, S);
       }
-      double invS = rcp(S);
+      double invS = rcp_raw(S);  // S = 0 (no predicted variance at all): the gain is NaN either way (0 * inf)
       mle_invS = invS;
 #pragma unroll
       for (int i = 0; i < N; ++i) {
@@ -1781,15 +1784,15 @@ __global__ void __launch_bounds__(THREADS * (1 + PAIR) + 64 * PIPE, (PIPE || PAI
             for (; c + THREADS < wd; c += 2 * THREADS) {
               const double ua = fma(-gain[0], s_zbuf[c], s_ubuf[c]);
               const double ub = fma(-gain[0], s_zbuf[c + THREADS], s_ubuf[c + THREADS]);
-              const double ra = err * rcp(fma(rtol, fabs(ua), atol));
-              const double rb = err * rcp(fma(rtol, fabs(ub), atol));
+              const double ra = err * rcp_raw(fma(rtol, fabs(ua), atol));
+              const double rb = err * rcp_raw(fma(rtol, fabs(ub), atol));
               part = fma(ra, ra, part);
               part = fma(rb, rb, part);
             }
           }
           for (; c < wd; c += THREADS) {
             const double u_new = fma(-gain[0], s_zbuf[c], s_ubuf[c]);
-            const double ratio = err * rcp(fma(rtol, fabs(u_new), atol));
+            const double ratio = err * rcp_raw(fma(rtol, fabs(u_new), atol));
             part = fma(ratio, ratio, part);
           }
         }
@@ -1798,11 +1801,11 @@ __global__ void __launch_bounds__(THREADS * (1 + PAIR) + 64 * PIPE, (PIPE || PAI
       } else if (GROUP == 1) {
 #pragma unroll
         for (int c = 0; c < D; ++c) {
-          double ratio = err * rcp(fma(rtol, fabs(m_new[0][c]), atol));
+          double ratio = err * rcp_raw(fma(rtol, fabs(m_new[0][c]), atol));
           acc = fma(ratio, ratio, acc);
         }
       } else {
-        double ratio = err * rcp(fma(rtol, fabs(m_new[0][0]), atol));
+        double ratio = err * rcp_raw(fma(rtol, fabs(m_new[0][0]), atol));
         acc = group_sum<GROUP>(real ? fma(ratio, ratio, 0.0) : 0.0, gmask);
       }
       e_norm = dsqrt(acc) * inv_sqrt_d;
