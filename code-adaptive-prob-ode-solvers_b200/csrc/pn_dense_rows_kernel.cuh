@@ -273,8 +273,9 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_rows_kernel(const __grid_
     double pn_[N], pinvn[N];
     {
       const double adt = fabs(dt);
-      const double sq = dsqrt(adt);
-      const double isq = rcp(sq), idt = rcp(adt);
+      // |dt| is a positive normal number: the unguarded fast paths are exact (as in pn_scalar_kernel.cuh)
+      const double sq = dsqrt_raw(adt);
+      const double isq = rcp_raw(sq), idt = rcp_raw(adt);
       double dtp = 1.0, idtp = 1.0;
 #pragma unroll
       for (int k = 0; k <= NU; ++k) {
@@ -350,7 +351,7 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_rows_kernel(const __grid_
       double yv[d];
 #pragma unroll
       for (int i = 0; i < d; ++i) {
-        const double inv = rcp(Rs[i * d + i]);
+        const double inv = rcp_raw(Rs[i * d + i]);
         double acc = zv[i];
 #pragma unroll
         for (int k = 0; k < i; ++k) acc = fma(-Rs[k * d + i], yv[k], acc);
@@ -424,7 +425,7 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_rows_kernel(const __grid_
       }
       if (FIX) {
         __syncwarp();
-        if (act) dinv[c] = rcp(W1[c * Dn + c]);
+        if (act) dinv[c] = rcp_raw(W1[c * Dn + c]);  // a zero pivot poisons the solve with NaN either way
         __syncwarp();
         // X = R11^{-1} R12, column cr
         double x[Dn];
@@ -555,7 +556,7 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_rows_kernel(const __grid_
         }
 #pragma unroll
         for (int i = 0; i < d; ++i) {
-          const double inv = rcp(Rs[i * d + i]);
+          const double inv = rcp_raw(Rs[i * d + i]);
           double acc = wt[i];
 #pragma unroll
           for (int k = 0; k < i; ++k) acc = fma(-Rs[k * d + i], y[k], acc);
@@ -563,7 +564,7 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_rows_kernel(const __grid_
         }
 #pragma unroll
         for (int i = d - 1; i >= 0; --i) {
-          const double inv = rcp(Rs[i * d + i]);
+          const double inv = rcp_raw(Rs[i * d + i]);
           double acc = y[i];
 #pragma unroll
           for (int k = i + 1; k < d; ++k) acc = fma(-Rs[i * d + k], gt[k], acc);
@@ -616,7 +617,7 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_rows_kernel(const __grid_
       double acc = 0.0;
 #pragma unroll
       for (int l = 0; l < d; ++l) {
-        const double ratio = errv[l] * rcp(fma(rtol, fabs(m_new[l]), atol));
+        const double ratio = errv[l] * rcp_raw(fma(rtol, fabs(m_new[l]), atol));
         acc = fma(ratio, ratio, acc);
       }
       e_norm = dsqrt(acc) * inv_sqrt_d;

@@ -482,9 +482,9 @@ __device__ __noinline__ void backward_warp(Mail<N>& M, const int nmain) {
           w = fma(BL[i][j], BR[i][c], w);
         }
         const double f = w * gg[j];
-        R12[j][c] = fma(-f, v0[j], 0.0);
+        R12[j][c] = fma(f, v0[j], 0.0);
 #pragma unroll
-        for (int i = 0; i < N; ++i) BR[i][c] = fma(-f, BL[i][j], BR[i][c]);
+        for (int i = 0; i < N; ++i) BR[i][c] = fma(f, BL[i][j], BR[i][c]);
       }
     }
     // X = RY^{-1} R12 (back substitution); G_p = X^T
@@ -565,12 +565,12 @@ __device__ __noinline__ void backward_warp(Mail<N>& M, const int nmain) {
 #pragma unroll
         for (int i = 0; i <= j; ++i) w = fma(Mb[i][j], Mb[i][c], w);
         w = fma(rf.v0, Mt[j][c], w);
-        const double f = w * rf.g;
-        Mt[j][c] = fma(-f, rf.v0, Mt[j][c]);
+        const double f = w * rf.ng;
+        Mt[j][c] = fma(f, rf.v0, Mt[j][c]);
 #pragma unroll
-        for (int i = j + 1; i < N; ++i) Mt[i][c] = fma(-f, Mt[i][j], Mt[i][c]);
+        for (int i = j + 1; i < N; ++i) Mt[i][c] = fma(f, Mt[i][j], Mt[i][c]);
 #pragma unroll
-        for (int i = 0; i <= j; ++i) Mb[i][c] = fma(-f, Mb[i][j], Mb[i][c]);
+        for (int i = 0; i <= j; ++i) Mb[i][c] = fma(f, Mb[i][j], Mb[i][c]);
       }
       Mt[j][j] = rf.beta;
     }
@@ -703,9 +703,9 @@ __device__ __noinline__ void backward_lanes(double* s_bw, double* s_job, int* s_
           wv = fma(BL[i][j], BR[i][c], wv);
         }
         const double f = wv * gg[j];
-        R12[j][c] = fma(-f, v0[j], 0.0);
+        R12[j][c] = fma(f, v0[j], 0.0);
 #pragma unroll
-        for (int i = 0; i < N; ++i) BR[i][c] = fma(-f, BL[i][j], BR[i][c]);
+        for (int i = 0; i < N; ++i) BR[i][c] = fma(f, BL[i][j], BR[i][c]);
       }
     }
     double X[N][N];
@@ -790,12 +790,12 @@ __device__ __noinline__ void backward_lanes(double* s_bw, double* s_job, int* s_
 #pragma unroll
           for (int i = 0; i <= j; ++i) wv = fma(Mb[i][j], Mb[i][c], wv);
           wv = fma(rf.v0, Mt[j][c], wv);
-          const double f = wv * rf.g;
-          Mt[j][c] = fma(-f, rf.v0, Mt[j][c]);
+          const double f = wv * rf.ng;
+          Mt[j][c] = fma(f, rf.v0, Mt[j][c]);
 #pragma unroll
-          for (int i = j + 1; i < N; ++i) Mt[i][c] = fma(-f, Mt[i][j], Mt[i][c]);
+          for (int i = j + 1; i < N; ++i) Mt[i][c] = fma(f, Mt[i][j], Mt[i][c]);
 #pragma unroll
-          for (int i = 0; i <= j; ++i) Mb[i][c] = fma(-f, Mb[i][j], Mb[i][c]);
+          for (int i = 0; i <= j; ++i) Mb[i][c] = fma(f, Mb[i][j], Mb[i][c]);
         }
         Mt[j][j] = rf.beta;
       }
@@ -1487,7 +1487,7 @@ __global__ void __launch_bounds__(THREADS * (1 + PAIR) + 64 * PIPE, (PIPE || PAI
         RY[j][j] = rf.beta;
         if constexpr (PIPE || PAIR) {
           pipe_v0[j] = rf.v0;
-          pipe_g[j] = rf.g;
+          pipe_g[j] = rf.ng;  // the NEGATED 2 / v^T v (see Reflector)
         }
         // left block columns c > j
 #pragma unroll
@@ -1497,10 +1497,10 @@ __global__ void __launch_bounds__(THREADS * (1 + PAIR) + 64 * PIPE, (PIPE || PAI
 #pragma unroll
           for (int i = 0; i < N; ++i) w = fma(BL[i][j], BL[i][c], w);
           w = fma(rf.v0, top, w);
-          double f = w * rf.g;
-          RY[j][c] = fma(-f, rf.v0, top);
+          double f = w * rf.ng;
+          RY[j][c] = fma(f, rf.v0, top);
 #pragma unroll
-          for (int i = 0; i < N; ++i) BL[i][c] = fma(-f, BL[i][j], BL[i][c]);
+          for (int i = 0; i < N; ++i) BL[i][c] = fma(f, BL[i][j], BL[i][c]);
         }
         if (FIX && !PIPE && !PAIR) {
           // right block columns: top entry starts at 0
@@ -1512,10 +1512,10 @@ __global__ void __launch_bounds__(THREADS * (1 + PAIR) + 64 * PIPE, (PIPE || PAI
               if (j == 0 && i > c) continue;  // still structurally zero
               w = fma(BL[i][j], BR[i][c], w);
             }
-            double f = w * rf.g;
-            R12[j][c] = fma(-f, rf.v0, 0.0);
+            double f = w * rf.ng;
+            R12[j][c] = fma(f, rf.v0, 0.0);
 #pragma unroll
-            for (int i = 0; i < N; ++i) BR[i][c] = fma(-f, BL[i][j], BR[i][c]);
+            for (int i = 0; i < N; ++i) BR[i][c] = fma(f, BL[i][j], BR[i][c]);
           }
         }
       }
@@ -1684,12 +1684,12 @@ __global__ void __launch_bounds__(THREADS * (1 + PAIR) + 64 * PIPE, (PIPE || PAI
 #pragma unroll
           for (int i = 0; i <= j; ++i) w = fma(Mb[i][j], Mb[i][c], w);
           w = fma(rf.v0, Mt[j][c], w);
-          double f = w * rf.g;
-          Mt[j][c] = fma(-f, rf.v0, Mt[j][c]);
+          double f = w * rf.ng;
+          Mt[j][c] = fma(f, rf.v0, Mt[j][c]);
 #pragma unroll
-          for (int i = j + 1; i < N; ++i) Mt[i][c] = fma(-f, Mt[i][j], Mt[i][c]);
+          for (int i = j + 1; i < N; ++i) Mt[i][c] = fma(f, Mt[i][j], Mt[i][c]);
 #pragma unroll
-          for (int i = 0; i <= j; ++i) Mb[i][c] = fma(-f, Mb[i][j], Mb[i][c]);
+          for (int i = 0; i <= j; ++i) Mb[i][c] = fma(f, Mb[i][j], Mb[i][c]);
         }
         Mt[j][j] = rf.beta;
       }
@@ -1724,10 +1724,10 @@ __global__ void __launch_bounds__(THREADS * (1 + PAIR) + 64 * PIPE, (PIPE || PAI
 #pragma unroll
         for (int i = c0 + 1; i <= Q; ++i) w = fma(Mc[i][c0], Mc[i][c], w);
         w = fma(rf.v0, Mc[c0][c], w);
-        double f = w * rf.g;
-        Mc[c0][c] = fma(-f, rf.v0, Mc[c0][c]);
+        double f = w * rf.ng;
+        Mc[c0][c] = fma(f, rf.v0, Mc[c0][c]);
 #pragma unroll
-        for (int i = c0 + 1; i <= Q; ++i) Mc[i][c] = fma(-f, Mc[i][c0], Mc[i][c]);
+        for (int i = c0 + 1; i <= Q; ++i) Mc[i][c] = fma(f, Mc[i][c0], Mc[i][c]);
       }
       Mc[c0][c0] = rf.beta;
     }
