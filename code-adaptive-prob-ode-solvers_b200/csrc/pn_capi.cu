@@ -406,6 +406,17 @@ __global__ void pn_selftest_math_kernel(const double* x, const double* y, double
   pw[i] = det_pow(fabs(x[i]), y[i]);
 }
 
+// out[8 i ..]: (v0, beta, g, ng) of make_reflector, then of the plain composition sqrt -> reciprocal
+__global__ void pn_selftest_reflector_kernel(const double* alpha, const double* sigma2, double* out, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Reflector a = make_reflector(alpha[i], sigma2[i]);
+  const Reflector b = make_reflector_plain(alpha[i], sigma2[i]);
+  double* o = out + 8 * i;
+  o[0] = a.v0, o[1] = a.beta, o[2] = a.g, o[3] = a.ng;
+  o[4] = b.v0, o[5] = b.beta, o[6] = b.g, o[7] = b.ng;
+}
+
 }  // namespace pn
 
 using namespace pn;
@@ -787,6 +798,12 @@ int pn_b200_trim(int device) {
 // Test hook (not part of the public header): evaluates the kernels' branch-free rcp / sqrt / pow.
 int pn_b200_selftest_math(const double* x, const double* y, double* r, double* sq, double* pw, long long n) {
   pn_selftest_math_kernel<<<(unsigned)((n + 255) / 256), 256>>>(x, y, r, sq, pw, n);
+  return cudaGetLastError() == cudaSuccess ? 0 : PN_B200_ERR_CUDA;
+}
+
+// Test hook: the Householder reflector scalars of the kernels next to their plain composition (8 doubles per input).
+int pn_b200_selftest_reflector(const double* alpha, const double* sigma2, double* out, long long n) {
+  pn_selftest_reflector_kernel<<<(unsigned)((n + 255) / 256), 256>>>(alpha, sigma2, out, n);
   return cudaGetLastError() == cudaSuccess ? 0 : PN_B200_ERR_CUDA;
 }
 

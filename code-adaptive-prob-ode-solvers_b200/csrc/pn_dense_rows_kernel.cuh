@@ -178,10 +178,10 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_rows_kernel(const __grid_
 #pragma unroll
       for (int i = j + 1; i < LIM; ++i) w = fma(v[i], rm[i], w);
       w = fma(R.v0, rm[j], w);
-      const double f = w * R.g;
-      const double nj = fma(-f, R.v0, rm[j]);
+      const double f = w * R.ng;
+      const double nj = fma(f, R.v0, rm[j]);
 #pragma unroll
-      for (int i = j + 1; i < LIM; ++i) rm[i] = fma(-f, v[i], rm[i]);
+      for (int i = j + 1; i < LIM; ++i) rm[i] = fma(f, v[i], rm[i]);
       rm[j] = (c == j) ? R.beta : nj;
     }
     if (c < d) {
@@ -405,18 +405,18 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_rows_kernel(const __grid_
           if (FIX) wr = fma(v[k], rb[k], wr);
         }
         wl = fma(R.v0, top_l, wl);
-        const double fl = wl * R.g;
-        const double ntop = fma(-fl, R.v0, top_l);
+        const double fl = wl * R.ng;
+        const double ntop = fma(fl, R.v0, top_l);
 #pragma unroll
-        for (int k = 0; k < Dn; ++k) lb[k] = fma(-fl, v[k], lb[k]);
+        for (int k = 0; k < Dn; ++k) lb[k] = fma(fl, v[k], lb[k]);
         const double r11 = (c == j) ? R.beta : ((c > j) ? ntop : 0.0);
         if (act) L_ext[c * Dn + j] = (c >= j) ? (pc * r11) : 0.0;
         if (FIX) {
           wr = fma(R.v0, 0.0, wr);
-          const double fr = wr * R.g;
-          const double rtop = fma(-fr, R.v0, 0.0);
+          const double fr = wr * R.ng;
+          const double rtop = fma(fr, R.v0, 0.0);
 #pragma unroll
-          for (int k = 0; k < Dn; ++k) rb[k] = fma(-fr, v[k], rb[k]);
+          for (int k = 0; k < Dn; ++k) rb[k] = fma(fr, v[k], rb[k]);
           if (act) {
             W1[j * Dn + c] = r11;
             W2[j * Dn + c] = rtop;
@@ -515,12 +515,12 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_rows_kernel(const __grid_
 #pragma unroll
           for (int k = 0; k <= j; ++k) w = fma(vl[k], bl[k], w);
           w = fma(R.v0, tt[j], w);
-          const double f = w * R.g;
-          const double nj = fma(-f, R.v0, tt[j]);
+          const double f = w * R.ng;
+          const double nj = fma(f, R.v0, tt[j]);
 #pragma unroll
-          for (int i = j + 1; i < Dn; ++i) tt[i] = fma(-f, vt[i], tt[i]);
+          for (int i = j + 1; i < Dn; ++i) tt[i] = fma(f, vt[i], tt[i]);
 #pragma unroll
-          for (int k = 0; k <= j; ++k) bl[k] = fma(-f, vl[k], bl[k]);
+          for (int k = 0; k <= j; ++k) bl[k] = fma(f, vl[k], bl[k]);
           tt[j] = (c == j) ? R.beta : nj;
         }
         if (act) {
@@ -599,10 +599,10 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_rows_kernel(const __grid_
 #pragma unroll
         for (int i = j + 1; i < LIM; ++i) w = fma(v[i], mc[i], w);
         w = fma(R.v0, mc[j], w);
-        const double f = w * R.g;
-        const double nj = fma(-f, R.v0, mc[j]);
+        const double f = w * R.ng;
+        const double nj = fma(f, R.v0, mc[j]);
 #pragma unroll
-        for (int i = j + 1; i < LIM; ++i) mc[i] = fma(-f, v[i], mc[i]);
+        for (int i = j + 1; i < LIM; ++i) mc[i] = fma(f, v[i], mc[i]);
         mc[j] = (c == j) ? R.beta : nj;
       }
       if (act && mode == MODE_STEP) {
