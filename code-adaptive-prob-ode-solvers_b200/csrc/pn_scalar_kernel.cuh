@@ -912,6 +912,8 @@ __global__ void __launch_bounds__(THREADS * (1 + PAIR) + 64 * PIPE, (PIPE || PAI
       }
       return pipe_ck_t;
     } else {
+      // (reusing the time the head of the iteration has loaded for the bookkeeping's first look at the same
+      // checkpoint was measured on the headline workload: no gain, more spills)
       return a.save_at[kc];
     }
   };
@@ -1015,7 +1017,9 @@ __global__ void __launch_bounds__(THREADS * (1 + PAIR) + 64 * PIPE, (PIPE || PAI
   double mle_ss = 0.0;  // solver_mle: sum over the accepted steps of z^T S^-1 z / d
   // utilisation statistics (per warp, flushed once at exit): loop iterations, lane-iterations with
   // work, lane-iterations spent on checkpoint interpolation
-  unsigned long long stat_warp_iters = 0, stat_lane_iters = 0, stat_interp_iters = 0;
+  // (32-bit, per lane: three 64-bit warp-uniform counters fed by a ballot + popc each lived in local memory and
+  // cost ~45 instructions and six local-memory round trips at the head of every iteration)
+  unsigned stat_warp_iters = 0, stat_lane_iters = 0, stat_interp_iters = 0;
   const long long clk0 = clock64();
 
   // solution.output_scale at checkpoint k: one value per IVP, one per dimension for blockdiag
@@ -1039,7 +1043,7 @@ __global__ void __launch_bounds__(THREADS * (1 + PAIR) + 64 * PIPE, (PIPE || PAI
     // ---- fetch a member ----------------------------------------------------------------
     // SLICE: a lane that has just lost its member looks for the next one at once; after an unsuccessful
     // look it only polls every eighth iteration (a poll is an L2 round trip that stalls the whole warp)
-    if (!have && !exhausted && (!SLICE || poll_now || (stat_warp_iters & 7ULL) == 0)) {
+    if (!have && !exhausted && (!SLICE || poll_now || (stat_warp_iters & 7u) == 0)) {
       unsigned long long tk = 0;
       bool resume = false, claimed_none = false;
       if constexpr (SLICE) {
@@ -1254,11 +1258,11 @@ __global__ void __launch_bounds__(THREADS * (1 + PAIR) + 64 * PIPE, (PIPE || PAI
     if constexpr (SLICE) {
       // belt and braces: every warp re-derives the queue mask from the counters once in a while, so a
       // parked member could not stay invisible even if no warp ever ran completely out of work
-      if ((stat_warp_iters & 4095ULL) == 0 && (threadIdx.x & 31) == 0)
+      if ((stat_warp_iters & 4095u) == 0 && (threadIdx.x & 31) == 0)
         slice_repair(&a, (int)((a.K - 2) >> a.slice_shift) + 1);
     }
-    stat_lane_iters += __popc(active);
-    stat_interp_iters += __popc(__ballot_sync(0xffffffffu, have && mode != MODE_STEP));
+    stat_lane_iters += have ? 1u : 0u;
+    stat_interp_iters += (have && mode != MODE_STEP) ? 1u : 0u;
     if constexpr (!PAIR) {
       if (!have) continue;  // idle lane
     }
@@ -2318,11 +2322,11 @@ __global__ void __launch_bounds__(THREADS * (1 + PAIR) + 64 * PIPE, (PIPE || PAI
     }
   }
   if ((threadIdx.x & 31) == 0) {
-    atomicAdd(a.ticket + 1, stat_warp_iters);
-    atomicAdd(a.ticket + 2, stat_lane_iters);
-    atomicAdd(a.ticket + 3, stat_interp_iters);
+    atomicAdd(a.ticket + 1, (unsigned long long)stat_warp_iters);
     atomicMax((long long*)a.ticket + 4, (long long)(clock64() - clk0));
   }
+  if (stat_lane_iters) atomicAdd(a.ticket + 2, (unsigned long long)stat_lane_iters);  // once per lane, at exit
+  if (stat_interp_iters) atomicAdd(a.ticket + 3, (unsigned long long)stat_interp_iters);
 #undef SBW
 #undef SPEND
 #undef SM
