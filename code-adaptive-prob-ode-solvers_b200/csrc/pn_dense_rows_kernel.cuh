@@ -617,7 +617,7 @@ __global__ void __launch_bounds__(32 * WARPS) pn_dense_rows_kernel(const __grid_
       double acc = 0.0;
 #pragma unroll
       for (int l = 0; l < d; ++l) {
-        const double ratio = errv[l] * rcp_raw(fma(rtol, fabs(m_new[l]), atol));
+        const double ratio = errv[l] * rcp(fma(rtol, fabs(m_new[l]), atol));
         acc = fma(ratio, ratio, acc);
       }
       e_norm = dsqrt(acc) * inv_sqrt_d;

@@ -1788,15 +1788,15 @@ __global__ void __launch_bounds__(THREADS * (1 + PAIR) + 64 * PIPE, (PIPE || PAI
             for (; c + THREADS < wd; c += 2 * THREADS) {
               const double ua = fma(-gain[0], s_zbuf[c], s_ubuf[c]);
               const double ub = fma(-gain[0], s_zbuf[c + THREADS], s_ubuf[c + THREADS]);
-              const double ra = err * rcp_raw(fma(rtol, fabs(ua), atol));
-              const double rb = err * rcp_raw(fma(rtol, fabs(ub), atol));
+              const double ra = err * rcp(fma(rtol, fabs(ua), atol));
+              const double rb = err * rcp(fma(rtol, fabs(ub), atol));
               part = fma(ra, ra, part);
               part = fma(rb, rb, part);
             }
           }
           for (; c < wd; c += THREADS) {
             const double u_new = fma(-gain[0], s_zbuf[c], s_ubuf[c]);
-            const double ratio = err * rcp_raw(fma(rtol, fabs(u_new), atol));
+            const double ratio = err * rcp(fma(rtol, fabs(u_new), atol));
             part = fma(ratio, ratio, part);
           }
         }
@@ -1805,11 +1805,13 @@ __global__ void __launch_bounds__(THREADS * (1 + PAIR) + 64 * PIPE, (PIPE || PAI
       } else if (GROUP == 1) {
 #pragma unroll
         for (int c = 0; c < D; ++c) {
-          double ratio = err * rcp_raw(fma(rtol, fabs(m_new[0][c]), atol));
+          double ratio = err * rcp(fma(rtol, fabs(m_new[0][c]), atol));
           acc = fma(ratio, ratio, acc);
         }
       } else {
-        double ratio = err * rcp_raw(fma(rtol, fabs(m_new[0][0]), atol));
+        // (guarded reciprocal: atol = 0 and a proposed u of exactly 0 must give an infinite error norm -- a rejected
+        // step, as in the oracle's division -- not a NaN, which would retire the member)
+        double ratio = err * rcp(fma(rtol, fabs(m_new[0][0]), atol));
         acc = group_sum<GROUP>(real ? fma(ratio, ratio, 0.0) : 0.0, gmask);
       }
       e_norm = dsqrt(acc) * inv_sqrt_d;
