@@ -352,6 +352,18 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+_JSON_FD = None  # the original stdout when file descriptor 1 has been pointed at stderr (N > 1)
+
+
+def _emit(line):
+    text = json.dumps(line) + "\n"
+    if _JSON_FD is None:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, text.encode())
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -375,6 +387,13 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        # stdout carries ONE JSON line: libraries that write to file descriptor 1 themselves (NCCL prints its version
+        # banner there at the first collective) are sent to stderr; the line goes to the original descriptor
+        sys.stdout.flush()
+        global _JSON_FD
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the solver has no CPU fallback")
     dev = torch.device(f"cuda:{local_rank}")
@@ -598,9 +617,9 @@ def main():
             line["parity_max_rel"] = worst
             line["parity_bit_exact"] = bool(exact and counts)
             if not (worst <= PARITY_TOL and counts):
-                print(json.dumps(line), flush=True)
+                _emit(line)
                 raise SystemExit(f"bench: GPU results differ from the oracle on the sampled members (max rel {worst:g}, counts equal: {counts})")
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
