@@ -184,3 +184,30 @@ def test_bench_reads_its_roofline_side_inputs_from_the_committed_ncu_summary():
     fetch = bench.ncu_instruction_fetch()
     assert fetch is not None and 0.5 < fetch["frac"] <= 1.0
     assert 0.05 < fetch["lines_refetched_per_instruction_line"] < 0.5
+
+
+def test_reference_arm_prints_one_json_line_with_the_contract_keys():
+    """`bench.py --impl reference` (the C port of the reference algorithm on the host cores) needs no GPU: exactly one
+    JSON line with the driver's keys, e2e equal to the line's own value and zero copy bytes."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        env.pop(k, None)
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--members", "64"], capture_output=True, text=True, env=env, timeout=600)  # fmt: skip
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.split("\n") if l.strip()]
+    assert len(lines) == 1, lines
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["metric"] == "ivp_solves_per_s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # a rank other than 0 under torchrun exits without work and without output
+    env.update(RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, env=env, timeout=600)  # fmt: skip
+    assert r.returncode == 0 and r.stdout.strip() == ""
