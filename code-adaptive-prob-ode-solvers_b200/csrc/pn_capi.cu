@@ -363,6 +363,14 @@ static int make_plan(const pn_b200_desc* d, Plan* p, bool need_device) {
     ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, p->k->solve_func, p->k->threads + p->k->extra_threads, p->smem);
     if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, cudaGetErrorString(ce));
     if (occ < 1) return fail(PN_B200_ERR_CUDA, "kernel does not fit on an SM");
+    // the time-sliced instantiation is a different kernel (its own register count): the persistent grid must be
+    // co-resident whichever of the two is launched
+    if (p->k->solve_func_sliced) {
+      int occ_sliced = 0;
+      ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sliced, p->k->solve_func_sliced, p->k->threads + p->k->extra_threads, p->smem);
+      if (ce != cudaSuccess) return fail(PN_B200_ERR_CUDA, cudaGetErrorString(ce));
+      if (occ_sliced >= 1 && occ_sliced < occ) occ = occ_sliced;
+    }
     p->ctas_per_sm = occ;
     std::lock_guard<std::mutex> lock(g_geom_mutex);
     g_geom.push_back({dev, p->k, p->smem, p->num_sms, occ});
